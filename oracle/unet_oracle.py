@@ -29,6 +29,38 @@ BN_EPS = 1e-5       # nn.BatchNorm2d default, unet/models/layers.py:33
 BN_MOMENTUM = 0.1   # nn.BatchNorm2d default
 
 
+# ------------------------------------------------------------------------------- storage model
+# The product stores activations (raw conv outputs and post-ReLU tensors) in bf16.  The
+# default oracle is pure fp32.  `bf16_storage()` makes the oracle round the same tensors to
+# bf16 (straight-through gradient), so ReLU / max-pool decisions are taken on identical values
+# and per-module input-gradient comparisons are not dominated by sign flips of near-zero
+# pre-activations (a flip fraction f costs sqrt(f) relative L2, ~6 % for f = 0.3 %).
+import contextlib
+
+_STORAGE_BF16 = False
+
+
+@contextlib.contextmanager
+def bf16_storage(enabled: bool = True):
+    global _STORAGE_BF16
+    old, _STORAGE_BF16 = _STORAGE_BF16, enabled
+    try:
+        yield
+    finally:
+        _STORAGE_BF16 = old
+
+
+def _st(t: Tensor) -> Tensor:
+    if not _STORAGE_BF16:
+        return t
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def _wq(w: Tensor) -> Tensor:
+    """Tensor-core operand: the product feeds bf16-rounded conv weights to the MMA."""
+    return _st(w)
+
+
 # ------------------------------------------------------------------------------- blocks
 def batch_norm(x: Tensor, sd: Dict[str, Tensor], p: str, training: bool) -> Tensor:
     """nn.BatchNorm2d (layers.py:33,36,153,159,165).  Train: biased batch variance to
@@ -52,8 +84,10 @@ def batch_norm(x: Tensor, sd: Dict[str, Tensor], p: str, training: bool) -> Tens
 def double_conv(x: Tensor, sd, p: str, training: bool) -> Tensor:
     """DoubleConv: (conv3x3 no-bias -> BN -> ReLU) x 2 (layers.py:31-38)."""
     for conv, bn in (("0", "1"), ("3", "4")):
-        x = F.conv2d(x, sd[f"{p}.double_conv.{conv}.weight"], None, 1, 1)
-        x = torch.relu(batch_norm(x, sd, f"{p}.double_conv.{bn}", training))
+        first_stem = conv == "0" and x.shape[1] % 16 != 0   # the stem conv runs in fp32 on CUDA cores
+        w = sd[f"{p}.double_conv.{conv}.weight"]
+        x = _st(F.conv2d(x, w if first_stem else _wq(w), None, 1, 1))
+        x = _st(torch.relu(batch_norm(x, sd, f"{p}.double_conv.{bn}", training)))
     return x
 
 
@@ -69,12 +103,17 @@ def bilinear_to(x: Tensor, size) -> Tensor:
 
 def attention_gate(g: Tensor, x: Tensor, sd, p: str, training: bool) -> Tensor:
     """AttentionGate.forward (layers.py:171-192): x * sigmoid(BN(psi(relu(BN(W_g up(g)) + BN(W_x x)))))."""
-    g_up = bilinear_to(g, x.shape[2:])
-    g1 = batch_norm(F.conv2d(g_up, sd[p + ".W_g.0.weight"]), sd, p + ".W_g.1", training)
-    x1 = batch_norm(F.conv2d(x, sd[p + ".W_x.0.weight"]), sd, p + ".W_x.1", training)
+    if _STORAGE_BF16:
+        # the product projects at low resolution (1x1 conv and bilinear resampling commute) and
+        # stores that projection in bf16
+        g1_raw = bilinear_to(_st(F.conv2d(g, _wq(sd[p + ".W_g.0.weight"]))), x.shape[2:])
+    else:
+        g1_raw = F.conv2d(bilinear_to(g, x.shape[2:]), sd[p + ".W_g.0.weight"])
+    g1 = batch_norm(g1_raw, sd, p + ".W_g.1", training)
+    x1 = batch_norm(_st(F.conv2d(x, _wq(sd[p + ".W_x.0.weight"]))), sd, p + ".W_x.1", training)
     s = torch.relu(g1 + x1)
     a = torch.sigmoid(batch_norm(F.conv2d(s, sd[p + ".psi.0.weight"]), sd, p + ".psi.1", training))
-    return x * a
+    return _st(x * a)
 
 
 def up_block(x1: Tensor, x2: Tensor, sd, p: str, attention: bool, bilinear: bool, training: bool) -> Tensor:
@@ -82,9 +121,9 @@ def up_block(x1: Tensor, x2: Tensor, sd, p: str, attention: bool, bilinear: bool
     The gate sees the *un-upsampled* decoder tensor; concat order is [skip, upsampled]."""
     skip = attention_gate(x1, x2, sd, p + ".attention", training) if attention else x2
     if bilinear:
-        up = bilinear_to(x1, (2 * x1.shape[2], 2 * x1.shape[3]))
+        up = _st(bilinear_to(x1, (2 * x1.shape[2], 2 * x1.shape[3])))
     else:
-        up = F.conv_transpose2d(x1, sd[p + ".up.weight"], sd[p + ".up.bias"], stride=2)
+        up = _st(F.conv_transpose2d(x1, _wq(sd[p + ".up.weight"]), sd[p + ".up.bias"], stride=2))
     dy, dx = skip.shape[2] - up.shape[2], skip.shape[3] - up.shape[3]
     up = F.pad(up, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
     return double_conv(torch.cat([skip, up], dim=1), sd, p + ".conv", training)

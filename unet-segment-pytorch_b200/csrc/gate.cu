@@ -1,0 +1,466 @@
+// Attention gate (AttentionGate.forward, unet/models/layers.py:171-192) as bandwidth-bound
+// passes around the two tcgen05 1x1 projections:
+//
+//   q  = W_g . g            (low resolution: the 1x1 conv commutes with bilinear resampling)
+//   xp = W_x . x            (full resolution, statistics in the conv epilogue)
+//   gate_upstats : batch statistics of up(q) for BN_g          (layers.py:153,183,186)
+//   gate_psi     : psi_raw = w_psi . relu(BN_g(up q) + BN_x(xp)) + its statistics (:188, :164)
+//   gate_apply   : a = sigmoid(BN_psi(psi_raw)); out = x * a   (:165-166, :192)
+// and the matching backward passes.  The three train-mode BatchNorms force three
+// grid-wide reductions, hence three phases; in eval mode the same kernels run with
+// folded running statistics and no reductions.
+//
+// Thread mapping: `tpp` (power of two <= 32) consecutive threads share a pixel and split its
+// 8-channel vectors; per-pixel channel reductions are shuffle reductions inside that group,
+// per-channel pixel reductions stay in registers (a thread's channels are fixed) and are
+// combined per block in shared memory, then across blocks by a finalize kernel in double.
+#include "../../include/unetb200.h"
+#include "conv.h"
+#include "resample.cuh"
+#include "vec.cuh"
+
+namespace ub2 {
+
+static constexpr int kGateThreads = 256;
+static constexpr int kMaxG = 2;  // 8-channel groups per thread (channels <= 512)
+
+struct GateGeom {
+  int N, H, W, C, cgs, tpp, slots;
+  long long pixels;
+  LowRes lr;
+};
+
+static int gate_tpp(int cgs) {
+  int t = 1;
+  while (t < cgs && t < 32) t *= 2;
+  return t;
+}
+static int make_gate_geom(GateGeom* g, int N, int H, int W, int C, int hin, int win) {
+  if (C % 8 != 0 || N <= 0 || H <= 0 || W <= 0) return UB2_ERR_SHAPE;
+  g->N = N; g->H = H; g->W = W; g->C = C; g->cgs = C / 8;
+  g->tpp = gate_tpp(g->cgs);
+  if ((g->cgs + g->tpp - 1) / g->tpp > kMaxG) return UB2_ERR_SHAPE;
+  g->slots = kGateThreads / g->tpp;
+  g->pixels = static_cast<long long>(N) * H * W;
+  g->lr = make_lowres(hin > 0 ? hin : 1, win > 0 ? win : 1, H, W);
+  return 0;
+}
+static int gate_grid(const GateGeom& g, int per_sm) {
+  return stream_grid(g.pixels, g.slots, num_sms(), per_sm);
+}
+
+__device__ __forceinline__ float group_sum(float v, int tpp) {
+  for (int o = tpp >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Reduce per-thread channel accumulators over the pixel slots of a block and write one
+// row of doubles: out_row[ns*C + channel].
+template <int NS>
+__device__ __forceinline__ void block_reduce_channels(float (&acc)[kMaxG][NS][8], const GateGeom& g,
+                                                      int slot, int j, double* out_row, float* smem) {
+#pragma unroll
+  for (int gi = 0; gi < kMaxG; ++gi) {
+#pragma unroll
+    for (int ns = 0; ns < NS; ++ns) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) smem[(slot * g.tpp + j) * 8 + k] = acc[gi][ns][k];
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < g.tpp * 8; idx += blockDim.x) {
+        const int jj = idx >> 3, k = idx & 7;
+        const int cg = jj + gi * g.tpp;
+        if (cg < g.cgs) {
+          double s = 0.0;
+          for (int sl = 0; sl < g.slots; ++sl) s += static_cast<double>(smem[(sl * g.tpp + jj) * 8 + k]);
+          out_row[static_cast<size_t>(ns) * g.C + cg * 8 + k] = s;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Same for per-thread scalars (NS values), written as out_row[ns].
+template <int NS>
+__device__ __forceinline__ void block_reduce_scalars(float (&acc)[NS], double* out_row, float* smem) {
+#pragma unroll
+  for (int ns = 0; ns < NS; ++ns) {
+    const float w = warp_sum(acc[ns]);
+    if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < (blockDim.x >> 5); ++i) s += static_cast<double>(smem[i]);
+      out_row[ns] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// Warp-uniform trip count (the shuffle reductions need every lane): `pv` masks the tail.
+#define GATE_PIXEL_LOOP(g)                                                                  \
+  const int slot = threadIdx.x / (g).tpp;                                                   \
+  const int j = threadIdx.x % (g).tpp;                                                      \
+  for (long long base = static_cast<long long>(blockIdx.x) * (g).slots; base < (g).pixels;  \
+       base += static_cast<long long>(gridDim.x) * (g).slots)
+
+#define GATE_PIX(g)                     \
+  const long long pix = base + slot;    \
+  const bool pv = pix < (g).pixels;
+
+#define GATE_DECODE(g)                                                        \
+  const int wo = static_cast<int>(pix % (g).W);                               \
+  const int ho = static_cast<int>((pix / (g).W) % (g).H);                     \
+  const int n = static_cast<int>(pix / (static_cast<long long>((g).W) * (g).H));
+
+// ------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(kGateThreads)
+gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* partials, GateGeom g) {
+  __shared__ float smem[kGateThreads * 8];
+  float acc[kMaxG][2][8];
+#pragma unroll
+  for (int a = 0; a < kMaxG; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[a][b][k] = 0.f;
+  GATE_PIXEL_LOOP(g) {
+    GATE_PIX(g)
+    GATE_DECODE(g)
+#pragma unroll
+    for (int gi = 0; gi < kMaxG; ++gi) {
+      const int cg = j + gi * g.tpp;
+      if (pv && cg < g.cgs) {
+        const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[gi][0][k] += u.v[k];
+          acc[gi][1][k] = fmaf(u.v[k], u.v[k], acc[gi][1][k]);
+        }
+      }
+    }
+  }
+  const int slot2 = threadIdx.x / g.tpp, j2 = threadIdx.x % g.tpp;
+  block_reduce_channels<2>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 2 * g.C, smem);
+}
+
+__global__ void __launch_bounds__(kGateThreads)
+gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat16* __restrict__ xp,
+                int ld_xp, const float* __restrict__ sg, const float* __restrict__ hg,
+                const float* __restrict__ sx, const float* __restrict__ hx,
+                const float* __restrict__ wpsi, float* __restrict__ psi_raw, double* partials,
+                GateGeom g) {
+  __shared__ float smem[kGateThreads / 32];
+  float st[2] = {0.f, 0.f};
+  GATE_PIXEL_LOOP(g) {
+    GATE_PIX(g)
+    GATE_DECODE(g)
+    float dot = 0.f;
+#pragma unroll
+    for (int gi = 0; gi < kMaxG; ++gi) {
+      const int cg = j + gi * g.tpp;
+      if (pv && cg < g.cgs) {
+        const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
+        const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = cg * 8 + k;
+          const float t = fmaf(u.v[k], __ldg(sg + c), __ldg(hg + c)) + fmaf(xv.v[k], __ldg(sx + c), __ldg(hx + c));
+          dot = fmaf(__ldg(wpsi + c), fmaxf(t, 0.f), dot);
+        }
+      }
+    }
+    dot = group_sum(dot, g.tpp);
+    if (pv && j == 0) {
+      psi_raw[pix] = dot;
+      st[0] += dot;
+      st[1] = fmaf(dot, dot, st[1]);
+    }
+  }
+  if (partials != nullptr) block_reduce_scalars<2>(st, partials + static_cast<size_t>(blockIdx.x) * 2, smem);
+}
+
+__global__ void __launch_bounds__(256)
+gate_apply_kernel(const float* __restrict__ psi_raw, const float* __restrict__ spsi,
+                  const float* __restrict__ hpsi, const __nv_bfloat16* __restrict__ x, int ld_x,
+                  __nv_bfloat16* __restrict__ out, int ld_out, float* __restrict__ a_out,
+                  long long pixels, int cgs) {
+  const float s = __ldg(spsi), h = __ldg(hpsi);
+  const long long total = pixels * cgs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cgs);
+    const long long pix = i / cgs;
+    const float z = fmaf(__ldg(psi_raw + pix), s, h);
+    const float a = 1.f / (1.f + __expf(-z));
+    F8 v = load8_stream(x + static_cast<size_t>(pix) * ld_x + cg * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] *= a;
+    store8(out + static_cast<size_t>(pix) * ld_out + cg * 8, v);
+    if (cg == 0 && a_out != nullptr) a_out[pix] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------ backward
+// da = sum_c dOut_c x_c ; d(BN_psi out) = da * a (1-a) ; dx_direct = dOut * a
+__global__ void __launch_bounds__(kGateThreads)
+gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_bfloat16* __restrict__ x,
+                  int ld_x, const float* __restrict__ a, const float* __restrict__ psi_raw,
+                  const float* __restrict__ mean_psi, const float* __restrict__ invstd_psi,
+                  __nv_bfloat16* __restrict__ dx, int ld_dx, float* __restrict__ dpsin,
+                  double* partials, GateGeom g) {
+  __shared__ float smem[kGateThreads / 32];
+  const float mu = __ldg(mean_psi), is = __ldg(invstd_psi);
+  float st[2] = {0.f, 0.f};
+  GATE_PIXEL_LOOP(g) {
+    GATE_PIX(g)
+    const float av = pv ? __ldg(a + pix) : 0.f;
+    float dot = 0.f;
+#pragma unroll
+    for (int gi = 0; gi < kMaxG; ++gi) {
+      const int cg = j + gi * g.tpp;
+      if (pv && cg < g.cgs) {
+        F8 d = load8_stream(dout + static_cast<size_t>(pix) * ld_do + cg * 8);
+        const F8 xv = load8_stream(x + static_cast<size_t>(pix) * ld_x + cg * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          dot = fmaf(d.v[k], xv.v[k], dot);
+          d.v[k] *= av;
+        }
+        store8(dx + static_cast<size_t>(pix) * ld_dx + cg * 8, d);
+      }
+    }
+    dot = group_sum(dot, g.tpp);
+    if (pv && j == 0) {
+      const float dn = dot * av * (1.f - av);
+      dpsin[pix] = dn;
+      st[0] += dn;
+      st[1] = fmaf(dn, (__ldg(psi_raw + pix) - mu) * is, st[1]);
+    }
+  }
+  block_reduce_scalars<2>(st, partials + static_cast<size_t>(blockIdx.x) * 2, smem);
+}
+
+// ds_c = dpsi_raw * w_psi_c * [t_c > 0]; channel sums: ds, ds*xhat_x, ds*xhat_g, dpsi_raw*relu(t)
+__global__ void __launch_bounds__(kGateThreads)
+gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi_raw,
+                  const float* __restrict__ coef_psi, const float* __restrict__ mean_psi,
+                  const float* __restrict__ invstd_psi, const __nv_bfloat16* __restrict__ q, int ld_q,
+                  const __nv_bfloat16* __restrict__ xp, int ld_xp, const float* __restrict__ sg,
+                  const float* __restrict__ hg, const float* __restrict__ sx,
+                  const float* __restrict__ hx, const float* __restrict__ mean_g,
+                  const float* __restrict__ invstd_g, const float* __restrict__ mean_x,
+                  const float* __restrict__ invstd_x, const float* __restrict__ wpsi,
+                  __nv_bfloat16* __restrict__ ds, int ld_ds, double* partials, GateGeom g) {
+  __shared__ float smem[kGateThreads * 8];
+  const float c1 = __ldg(coef_psi), c2 = __ldg(coef_psi + 1), c3 = __ldg(coef_psi + 2);
+  const float mu = __ldg(mean_psi), is = __ldg(invstd_psi);
+  float acc[kMaxG][4][8];
+#pragma unroll
+  for (int a = 0; a < kMaxG; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[a][b][k] = 0.f;
+  GATE_PIXEL_LOOP(g) {
+    GATE_PIX(g)
+    GATE_DECODE(g)
+    const float ph = pv ? (__ldg(psi_raw + pix) - mu) * is : 0.f;
+    const float dpr = pv ? c1 * (__ldg(dpsin + pix) - c2 - ph * c3) : 0.f;
+#pragma unroll
+    for (int gi = 0; gi < kMaxG; ++gi) {
+      const int cg = j + gi * g.tpp;
+      if (pv && cg < g.cgs) {
+        const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
+        const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
+        F8 o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = cg * 8 + k;
+          const float t = fmaf(u.v[k], __ldg(sg + c), __ldg(hg + c)) + fmaf(xv.v[k], __ldg(sx + c), __ldg(hx + c));
+          const float d = (t > 0.f) ? dpr * __ldg(wpsi + c) : 0.f;
+          o.v[k] = d;
+          acc[gi][0][k] += d;
+          acc[gi][1][k] = fmaf(d, (xv.v[k] - __ldg(mean_x + c)) * __ldg(invstd_x + c), acc[gi][1][k]);
+          acc[gi][2][k] = fmaf(d, (u.v[k] - __ldg(mean_g + c)) * __ldg(invstd_g + c), acc[gi][2][k]);
+          acc[gi][3][k] = fmaf(dpr, fmaxf(t, 0.f), acc[gi][3][k]);
+        }
+        store8(ds + static_cast<size_t>(pix) * ld_ds + cg * 8, o);
+      }
+    }
+  }
+  const int slot2 = threadIdx.x / g.tpp, j2 = threadIdx.x % g.tpp;
+  block_reduce_channels<4>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 4 * g.C, smem);
+}
+
+// coef rows: 0..2 = BN_x {gamma*invstd, sum(ds)/M, sum(ds*xhat_x)/M}; 3..5 = BN_g
+__global__ void gate_bwd_finalize_kernel(const double* __restrict__ partials, int rows, int C,
+                                         double count, const float* __restrict__ gamma_x,
+                                         const float* __restrict__ invstd_x,
+                                         const float* __restrict__ gamma_g,
+                                         const float* __restrict__ invstd_g, float* dgamma_x,
+                                         float* dbeta_x, float* dgamma_g, float* dbeta_g, float* dwpsi,
+                                         float* coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < 4; ++k) s[k] += partials[(static_cast<size_t>(r) * 4 + k) * C + c];
+  if (dbeta_x) dbeta_x[c] += static_cast<float>(s[0]);
+  if (dgamma_x) dgamma_x[c] += static_cast<float>(s[1]);
+  if (dbeta_g) dbeta_g[c] += static_cast<float>(s[0]);
+  if (dgamma_g) dgamma_g[c] += static_cast<float>(s[2]);
+  if (dwpsi) dwpsi[c] += static_cast<float>(s[3]);
+  coef[0 * C + c] = gamma_x[c] * invstd_x[c];
+  coef[1 * C + c] = static_cast<float>(s[0] / count);
+  coef[2 * C + c] = static_cast<float>(s[1] / count);
+  coef[3 * C + c] = gamma_g[c] * invstd_g[c];
+  coef[4 * C + c] = static_cast<float>(s[0] / count);
+  coef[5 * C + c] = static_cast<float>(s[2] / count);
+}
+
+// dxp = BN_x backward of ds; dgup = BN_g backward of ds (full resolution, later up-sample^T)
+__global__ void __launch_bounds__(256)
+gate_bwd_xg_kernel(const __nv_bfloat16* __restrict__ ds, int ld_ds, const __nv_bfloat16* __restrict__ xp,
+                   int ld_xp, const __nv_bfloat16* __restrict__ q, int ld_q,
+                   const float* __restrict__ mean_x, const float* __restrict__ invstd_x,
+                   const float* __restrict__ mean_g, const float* __restrict__ invstd_g,
+                   const float* __restrict__ coef, __nv_bfloat16* __restrict__ dxp, int ld_dxp,
+                   __nv_bfloat16* __restrict__ dgup, int ld_dg, GateGeom g) {
+  const long long total = g.pixels * g.cgs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % g.cgs);
+    const long long pix = i / g.cgs;
+    GATE_DECODE(g)
+    const F8 d = load8_stream(ds + static_cast<size_t>(pix) * ld_ds + cg * 8);
+    const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
+    const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
+    F8 ox, og;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cg * 8 + k;
+      const float xh = (xv.v[k] - __ldg(mean_x + c)) * __ldg(invstd_x + c);
+      const float gh = (u.v[k] - __ldg(mean_g + c)) * __ldg(invstd_g + c);
+      ox.v[k] = __ldg(coef + c) * (d.v[k] - __ldg(coef + g.C + c) - xh * __ldg(coef + 2 * g.C + c));
+      og.v[k] = __ldg(coef + 3 * g.C + c) * (d.v[k] - __ldg(coef + 4 * g.C + c) - gh * __ldg(coef + 5 * g.C + c));
+    }
+    store8(dxp + static_cast<size_t>(pix) * ld_dxp + cg * 8, ox);
+    store8(dgup + static_cast<size_t>(pix) * ld_dg + cg * 8, og);
+  }
+}
+
+}  // namespace ub2
+
+using namespace ub2;
+typedef const __nv_bfloat16* cbf;
+typedef __nv_bfloat16* bf;
+
+extern "C" {
+
+int ub2_gate_rows(int N, int H, int W, int C) {
+  GateGeom g;
+  int rc = make_gate_geom(&g, N, H, W, C, 1, 1);
+  if (rc) return rc;
+  return gate_grid(g, 4);
+}
+
+int ub2_gate_upstats(const void* q, int ld_q, int N, int hin, int win, int H, int W, int Ci,
+                     double* partials, int rows, void* stream) {
+  GateGeom g;
+  int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
+  if (rc) return rc;
+  const int grid = gate_grid(g, 4);
+  if (grid != rows) return UB2_ERR_WORKSPACE;
+  gate_upstats_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<cbf>(q), ld_q, partials, g);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_gate_psi(const void* q, int ld_q, const void* xp, int ld_xp, const float* scale_g,
+                 const float* shift_g, const float* scale_x, const float* shift_x, const float* wpsi,
+                 float* psi_raw, double* partials, int rows, int N, int hin, int win, int H, int W,
+                 int Ci, void* stream) {
+  GateGeom g;
+  int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
+  if (rc) return rc;
+  const int grid = gate_grid(g, 4);
+  if (partials != nullptr && grid != rows) return UB2_ERR_WORKSPACE;
+  gate_psi_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi,
+      psi_raw, partials, g);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_gate_apply(const float* psi_raw, const float* scale_psi, const float* shift_psi, const void* x,
+                   int ld_x, void* out, int ld_out, float* a_out, int N, int H, int W, int Cx,
+                   void* stream) {
+  if (Cx % 8 != 0 || N <= 0) return UB2_ERR_SHAPE;
+  const long long pixels = static_cast<long long>(N) * H * W;
+  gate_apply_kernel<<<stream_grid(pixels * (Cx / 8), 256, num_sms()), 256, 0,
+                      static_cast<cudaStream_t>(stream)>>>(
+      psi_raw, scale_psi, shift_psi, static_cast<cbf>(x), ld_x, static_cast<bf>(out), ld_out, a_out,
+      pixels, Cx / 8);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_gate_bwd_a(const void* dout, int ld_do, const void* x, int ld_x, const float* a,
+                   const float* psi_raw, const float* mean_psi, const float* invstd_psi, void* dx,
+                   int ld_dx, float* dpsin, double* partials, int rows, int N, int H, int W, int Cx,
+                   void* stream) {
+  GateGeom g;
+  int rc = make_gate_geom(&g, N, H, W, Cx, 1, 1);
+  if (rc) return rc;
+  const int grid = gate_grid(g, 4);
+  if (grid != rows) return UB2_ERR_WORKSPACE;
+  gate_bwd_a_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, mean_psi, invstd_psi,
+      static_cast<bf>(dx), ld_dx, dpsin, partials, g);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_psi,
+                   const float* mean_psi, const float* invstd_psi, const void* q, int ld_q,
+                   const void* xp, int ld_xp, const float* scale_g, const float* shift_g,
+                   const float* scale_x, const float* shift_x, const float* mean_g,
+                   const float* invstd_g, const float* mean_x, const float* invstd_x,
+                   const float* wpsi, void* ds, int ld_ds, double* partials, int rows, int N, int hin,
+                   int win, int H, int W, int Ci, void* stream) {
+  GateGeom g;
+  int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
+  if (rc) return rc;
+  const int grid = gate_grid(g, 4);
+  if (grid != rows) return UB2_ERR_WORKSPACE;
+  gate_bwd_s_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      dpsin, psi_raw, coef_psi, mean_psi, invstd_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp),
+      ld_xp, scale_g, shift_g, scale_x, shift_x, mean_g, invstd_g, mean_x, invstd_x, wpsi,
+      static_cast<bf>(ds), ld_ds, partials, g);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_gate_bwd_finalize(const double* partials, int rows, int Ci, double count, const float* gamma_x,
+                          const float* invstd_x, const float* gamma_g, const float* invstd_g,
+                          float* dgamma_x, float* dbeta_x, float* dgamma_g, float* dbeta_g,
+                          float* dwpsi, float* coef, void* stream) {
+  if (Ci <= 0 || rows <= 0) return UB2_ERR_SHAPE;
+  gate_bwd_finalize_kernel<<<(Ci + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, rows, Ci, count, gamma_x, invstd_x, gamma_g, invstd_g, dgamma_x, dbeta_x, dgamma_g,
+      dbeta_g, dwpsi, coef);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_gate_bwd_xg(const void* ds, int ld_ds, const void* xp, int ld_xp, const void* q, int ld_q,
+                    const float* mean_x, const float* invstd_x, const float* mean_g,
+                    const float* invstd_g, const float* coef, void* dxp, int ld_dxp, void* dgup,
+                    int ld_dg, int N, int hin, int win, int H, int W, int Ci, void* stream) {
+  GateGeom g;
+  int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
+  if (rc) return rc;
+  gate_bwd_xg_kernel<<<stream_grid(g.pixels * g.cgs, 256, num_sms()), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(
+      static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp, static_cast<cbf>(q), ld_q, mean_x,
+      invstd_x, mean_g, invstd_g, coef, static_cast<bf>(dxp), ld_dxp, static_cast<bf>(dgup), ld_dg, g);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -1,0 +1,388 @@
+// The two ends of the network, both far below the tensor-core ridge:
+//
+//  * conv_in: the first 3x3 convolution (inc.double_conv.0, layers.py:32) with Cin = n_channels
+//    (1 for CT slices): K = 9*Cin, arithmetic intensity ~9 flop/B -> a direct fp32 CUDA-core
+//    convolution reading the fp32 NCHW input and writing NHWC bf16 + BatchNorm statistics,
+//    and its weight gradient (no data gradient: the input needs none).
+//  * outc: OutConv's 1x1 conv with bias (layers.py:120) C -> n_classes, writing fp32 NCHW
+//    logits, and its backward (data gradient NHWC bf16, weight / bias gradients).
+#include "../../include/unetb200.h"
+#include "conv.h"
+#include "vec.cuh"
+
+namespace ub2 {
+
+static constexpr int kHeadThreads = 256;
+static constexpr int kMaxClasses = 8;
+static constexpr int kMaxCin = 4;
+
+// ------------------------------------------------------------------------------ conv_in
+__global__ void __launch_bounds__(kHeadThreads)
+conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                   int ld_y, double* partials, int N, int Cin, int H, int W, int Cout) {
+  extern __shared__ float s_dyn[];
+  float* s_w = s_dyn;                         // [Cin*9][Cout]
+  float* s_red = s_dyn + Cin * 9 * Cout;      // [lanes][cgs][16]
+  for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) {
+    const int co = i / (Cin * 9), r = i % (Cin * 9);
+    s_w[r * Cout + co] = w[i];
+  }
+  __syncthreads();
+  const int cgs = Cout / 8;
+  const int lanes = blockDim.x / cgs;
+  const int lane = threadIdx.x / cgs, cg = threadIdx.x % cgs;
+  const bool active = lane < lanes;
+  const long long pixels = static_cast<long long>(N) * H * W;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  if (active) {
+    for (long long pix = static_cast<long long>(blockIdx.x) * lanes + lane; pix < pixels;
+         pix += static_cast<long long>(gridDim.x) * lanes) {
+      const int wq = static_cast<int>(pix % W);
+      const int hq = static_cast<int>((pix / W) % H);
+      const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float* xp = x + (static_cast<size_t>(n) * Cin + ci) * H * W;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
+          const float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xp + static_cast<size_t>(hh) * W + ww) : 0.f;
+          const float* wr = s_w + (ci * 9 + t) * Cout + cg * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wr[k], acc[k]);
+        }
+      }
+      F8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
+      const uint4 packed = pack8(o);
+      *reinterpret_cast<uint4*>(y + static_cast<size_t>(pix) * ld_y + cg * 8) = packed;
+      const F8 r = unpack8(packed);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s1[k] += r.v[k];
+        s2[k] = fmaf(r.v[k], r.v[k], s2[k]);
+      }
+    }
+  }
+  if (partials != nullptr) {
+    float* mine = s_red + (static_cast<size_t>(lane) * cgs + cg) * 16;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { mine[k] = s1[k]; mine[8 + k] = s2[k]; }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cgs * 16; idx += blockDim.x) {
+      double a = 0.0;
+      for (int l = 0; l < lanes; ++l) a += static_cast<double>(s_red[static_cast<size_t>(l) * cgs * 16 + idx]);
+      const int cgi = idx / 16, k = idx % 16;
+      partials[(static_cast<size_t>(blockIdx.x) * 2 + (k >> 3)) * Cout + cgi * 8 + (k & 7)] = a;
+    }
+  }
+}
+
+// dW[co][ci][t] = sum_p dy[p][co] * x[p + shift_t][ci]; blockIdx.y = ci; rows of [9][Cout] doubles
+__global__ void __launch_bounds__(kHeadThreads)
+conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int ld_dy,
+                     double* partials, int N, int Cin, int H, int W, int Cout) {
+  extern __shared__ float s_red[];  // [lanes][cgs][8]
+  const int ci = blockIdx.y;
+  const int cgs = Cout / 8;
+  const int lanes = blockDim.x / cgs;
+  const int lane = threadIdx.x / cgs, cg = threadIdx.x % cgs;
+  const bool active = lane < lanes;
+  const long long pixels = static_cast<long long>(N) * H * W;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  if (active) {
+    for (long long pix = static_cast<long long>(blockIdx.x) * lanes + lane; pix < pixels;
+         pix += static_cast<long long>(gridDim.x) * lanes) {
+      const int wq = static_cast<int>(pix % W);
+      const int hq = static_cast<int>((pix / W) % H);
+      const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+      const F8 d = load8_stream(dy + static_cast<size_t>(pix) * ld_dy + cg * 8);
+      const float* xp = x + (static_cast<size_t>(n) * Cin + ci) * H * W;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
+        const float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xp + static_cast<size_t>(hh) * W + ww) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[t][k] = fmaf(xv, d.v[k], acc[t][k]);
+      }
+    }
+  }
+  double* row = partials + (static_cast<size_t>(blockIdx.x) * Cin + ci) * 9 * Cout;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float* mine = s_red + (static_cast<size_t>(lane) * cgs + cg) * 8;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mine[k] = acc[t][k];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cgs * 8; idx += blockDim.x) {
+      double a = 0.0;
+      for (int l = 0; l < lanes; ++l) a += static_cast<double>(s_red[static_cast<size_t>(l) * cgs * 8 + idx]);
+      row[t * Cout + idx] = a;
+    }
+    __syncthreads();
+  }
+}
+
+// grad[co][ci][t] += sum_rows partials[row][ci][t][co]
+__global__ void conv_in_wgrad_finalize_kernel(const double* __restrict__ partials, int rows, int Cin,
+                                              int Cout, float* grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * Cin * 9) return;
+  const int co = i / (Cin * 9), r = i % (Cin * 9);
+  double a = 0.0;
+  for (int row = 0; row < rows; ++row) a += partials[(static_cast<size_t>(row) * Cin * 9 + r) * Cout + co];
+  grad[i] += static_cast<float>(a);
+}
+
+// ------------------------------------------------------------------------------ outc
+struct HeadGeom {
+  int C, cgs, tpp, slots, K;
+  long long pixels, HW;
+};
+
+__global__ void __launch_bounds__(kHeadThreads)
+outc_fwd_kernel(const __nv_bfloat16* __restrict__ a, int ld_a, const float* __restrict__ w,
+                const float* __restrict__ bias, float* __restrict__ logits, HeadGeom g) {
+  const int slot = threadIdx.x / g.tpp, j = threadIdx.x % g.tpp;
+  for (long long base = static_cast<long long>(blockIdx.x) * g.slots; base < g.pixels;
+       base += static_cast<long long>(gridDim.x) * g.slots) {
+    const long long pix = base + slot;
+    const bool pv = pix < g.pixels;
+    float dot[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) dot[k] = 0.f;
+    for (int cg = j; cg < g.cgs; cg += g.tpp) {
+      if (pv) {
+        const F8 v = load8_stream(a + static_cast<size_t>(pix) * ld_a + cg * 8);
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) {
+          if (k < g.K) {
+            const F8 wv = loadf8(w + static_cast<size_t>(k) * g.C + cg * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot[k] = fmaf(v.v[i], wv.v[i], dot[k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      if (k < g.K) {
+        for (int o = g.tpp >> 1; o > 0; o >>= 1) dot[k] += __shfl_xor_sync(0xffffffffu, dot[k], o);
+      }
+    }
+    if (pv && j == 0) {
+      const long long n = pix / g.HW, r = pix % g.HW;
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k)
+        if (k < g.K) logits[(n * g.K + k) * g.HW + r] = dot[k] + (bias ? __ldg(bias + k) : 0.f);
+    }
+  }
+}
+
+// dA[p][c] = sum_k dl[k][p] W[k][c];  partial rows: [K][C] (dW) then [K] (db), as doubles
+__global__ void __launch_bounds__(kHeadThreads)
+outc_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int ld_a,
+                const float* __restrict__ w, __nv_bfloat16* __restrict__ da, int ld_da,
+                double* partials, HeadGeom g) {
+  extern __shared__ float s_red[];  // [256][8]
+  const int slot = threadIdx.x / g.tpp, j = threadIdx.x % g.tpp;
+  // up to 2 channel groups per thread (C <= 512)
+  float accw[2][kMaxClasses][8];
+  float accb[kMaxClasses];
+#pragma unroll
+  for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) accw[gi][k][i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) accb[k] = 0.f;
+  for (long long base = static_cast<long long>(blockIdx.x) * g.slots; base < g.pixels;
+       base += static_cast<long long>(gridDim.x) * g.slots) {
+    const long long pix = base + slot;
+    if (pix >= g.pixels) continue;
+    const long long n = pix / g.HW, r = pix % g.HW;
+    float d[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      d[k] = (k < g.K) ? __ldg(dl + (n * g.K + k) * g.HW + r) : 0.f;
+      if (j == 0) accb[k] += d[k];
+    }
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+      const int cg = j + gi * g.tpp;
+      if (cg < g.cgs) {
+        const F8 v = load8_stream(a + static_cast<size_t>(pix) * ld_a + cg * 8);
+        F8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) {
+          if (k < g.K) {
+            const F8 wv = loadf8(w + static_cast<size_t>(k) * g.C + cg * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o.v[i] = fmaf(d[k], wv.v[i], o.v[i]);
+              accw[gi][k][i] = fmaf(d[k], v.v[i], accw[gi][k][i]);
+            }
+          }
+        }
+        if (da != nullptr) store8(da + static_cast<size_t>(pix) * ld_da + cg * 8, o);
+      }
+    }
+  }
+  double* row = partials + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(g.K) * g.C + g.K);
+#pragma unroll
+  for (int gi = 0; gi < 2; ++gi) {
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      if (k >= g.K) continue;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_red[(slot * g.tpp + j) * 8 + i] = accw[gi][k][i];
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < g.tpp * 8; idx += blockDim.x) {
+        const int jj = idx >> 3, i = idx & 7;
+        const int cg = jj + gi * g.tpp;
+        if (cg < g.cgs) {
+          double s = 0.0;
+          for (int sl = 0; sl < g.slots; ++sl) s += static_cast<double>(s_red[(sl * g.tpp + jj) * 8 + i]);
+          row[static_cast<size_t>(k) * g.C + cg * 8 + i] = s;
+        }
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    if (k >= g.K) continue;
+    const float ws = warp_sum(accb[k]);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ws;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < (blockDim.x >> 5); ++i) s += static_cast<double>(s_red[i]);
+      row[static_cast<size_t>(g.K) * g.C + k] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void outc_bwd_finalize_kernel(const double* __restrict__ partials, int rows, int K, int C,
+                                         float* dw, float* db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = K * C + K;
+  if (i >= total) return;
+  double a = 0.0;
+  for (int r = 0; r < rows; ++r) a += partials[static_cast<size_t>(r) * total + i];
+  if (i < K * C) {
+    if (dw) dw[i] += static_cast<float>(a);
+  } else if (db) {
+    db[i - K * C] += static_cast<float>(a);
+  }
+}
+
+static int head_geom(HeadGeom* g, int N, int H, int W, int C, int K) {
+  if (C % 8 != 0 || K < 1 || K > kMaxClasses || N <= 0) return UB2_ERR_SHAPE;
+  g->C = C; g->cgs = C / 8; g->K = K;
+  int t = 1;
+  while (t < g->cgs && t < 32) t *= 2;
+  g->tpp = t;
+  g->slots = kHeadThreads / t;
+  g->HW = static_cast<long long>(H) * W;
+  g->pixels = g->HW * N;
+  return 0;
+}
+
+}  // namespace ub2
+
+using namespace ub2;
+
+extern "C" {
+
+int ub2_conv_in_rows(int N, int H, int W, int Cout) {
+  if (Cout % 8 != 0 || Cout / 8 > kHeadThreads) return UB2_ERR_SHAPE;
+  const int lanes = kHeadThreads / (Cout / 8);
+  return stream_grid(static_cast<long long>(N) * H * W, lanes, num_sms(), 4);
+}
+
+int ub2_conv_in_fwd(const float* x, const float* w, void* y, int ld_y, double* partials, int rows, int N,
+                    int Cin, int H, int W, int Cout, void* stream) {
+  if (Cout % 8 != 0 || Cout / 8 > kHeadThreads || Cin < 1 || Cin > kMaxCin) return UB2_ERR_SHAPE;
+  const int cgs = Cout / 8;
+  const int block = cgs * (kHeadThreads / cgs);
+  const int lanes = block / cgs;
+  const int grid = stream_grid(static_cast<long long>(N) * H * W, lanes, num_sms(), 4);
+  if (partials != nullptr && grid != rows) return UB2_ERR_WORKSPACE;
+  const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + static_cast<size_t>(lanes) * cgs * 16) * sizeof(float);
+  conv_in_fwd_kernel<<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, Cin, H, W, Cout);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_conv_in_wgrad(const float* x, const void* dy, int ld_dy, double* partials, int rows, float* grad,
+                      int N, int Cin, int H, int W, int Cout, void* stream) {
+  if (Cout % 8 != 0 || Cout / 8 > kHeadThreads || Cin < 1 || Cin > kMaxCin) return UB2_ERR_SHAPE;
+  const int cgs = Cout / 8;
+  const int block = cgs * (kHeadThreads / cgs);
+  const int lanes = block / cgs;
+  const int grid = stream_grid(static_cast<long long>(N) * H * W, lanes, num_sms(), 4);
+  if (grid != rows) return UB2_ERR_WORKSPACE;
+  const size_t smem = static_cast<size_t>(lanes) * cgs * 8 * sizeof(float);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  conv_in_wgrad_kernel<<<dim3(grid, Cin), block, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dy),
+                                                           ld_dy, partials, N, Cin, H, W, Cout);
+  const int total = Cout * Cin * 9;
+  conv_in_wgrad_finalize_kernel<<<(total + 127) / 128, 128, 0, s>>>(partials, grid, Cin, Cout, grad);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_outc_rows(int N, int H, int W, int C) {
+  HeadGeom g;
+  int rc = head_geom(&g, N, H, W, C, 1);
+  if (rc) return rc;
+  return stream_grid(g.pixels, g.slots, num_sms(), 4);
+}
+
+int ub2_outc_fwd(const void* a, int ld_a, const float* w, const float* bias, float* logits, int N, int H,
+                 int W, int C, int K, void* stream) {
+  HeadGeom g;
+  int rc = head_geom(&g, N, H, W, C, K);
+  if (rc) return rc;
+  outc_fwd_kernel<<<stream_grid(g.pixels, g.slots, num_sms(), 8), kHeadThreads, 0,
+                    static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), ld_a, w,
+                                                        bias, logits, g);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_outc_bwd(const float* dlogits, const void* a, int ld_a, const float* w, void* da, int ld_da,
+                 double* partials, int rows, float* dw, float* db, int N, int H, int W, int C, int K,
+                 void* stream) {
+  HeadGeom g;
+  int rc = head_geom(&g, N, H, W, C, K);
+  if (rc) return rc;
+  if (g.cgs > 2 * g.tpp) return UB2_ERR_SHAPE;
+  const int grid = stream_grid(g.pixels, g.slots, num_sms(), 4);
+  if (grid != rows) return UB2_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  outc_bwd_kernel<<<grid, kHeadThreads, kHeadThreads * 8 * sizeof(float), s>>>(
+      dlogits, static_cast<const __nv_bfloat16*>(a), ld_a, w, static_cast<__nv_bfloat16*>(da), ld_da,
+      partials, g);
+  const int total = K * C + K;
+  outc_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, s>>>(partials, grid, K, C, dw, db);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

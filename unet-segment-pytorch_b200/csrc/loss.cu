@@ -1,0 +1,201 @@
+// Segmentation-loss statistics and their gradient (DiceLoss / BalancedCELoss / DiceBCELoss,
+// unet/utils/loss.py:45-85, :110-150, :184-191).
+//
+// Both reference losses are functions of four per-(image, class) sums over the pixels:
+//   cnt[n,c]  = #{i : t_i = c}                      (loss.py:139-140, F.one_hot sum :71)
+//   ce[n,c]   = sum_{i : t_i = c} -log softmax(z_i)[c]   (F.cross_entropy, :129, split by class)
+//   I[n,c]    = sum_{i : t_i = c} softmax(z_i)[c]        (intersection, :70)
+//   P[n,c]    = sum_i softmax(z_i)[c]                    (:71)
+// seg_stats computes them in one pass over the fp32 NCHW logits + int64 targets with
+// warp-shuffle reductions (16 B/pixel for 2 classes); the O(N*C) combination into the scalar
+// loss stays on the host side of the ABI.  seg_stats_bwd is the second pass:
+//   dz[i,k] = dce[n,t_i] (p_ik - y_ik) + p_ik (g_ik - sum_c g_ic p_ic),
+//   g_ic = dI[n,c] [t_i = c] + dP[n,c]
+#include "../../include/unetb200.h"
+#include "conv.h"
+#include "vec.cuh"
+
+namespace ub2 {
+
+static constexpr int kLossThreads = 256;
+static constexpr int kLossMaxC = 8;
+
+template <int C>
+__device__ __forceinline__ void softmax_px(const float* __restrict__ z, long long HW, long long r,
+                                           float (&p)[C], float& lse) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    p[c] = __ldg(z + c * HW + r);
+    m = fmaxf(m, p[c]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    p[c] = expf(p[c] - m);
+    s += p[c];
+  }
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int c = 0; c < C; ++c) p[c] *= inv;
+  lse = m + logf(s);
+}
+
+// grid = (blocks_per_image, N); partial rows: [n][block][C][4] doubles
+template <int C>
+__global__ void __launch_bounds__(kLossThreads)
+seg_stats_kernel(const float* __restrict__ logits, const long long* __restrict__ targets, long long HW,
+                 double* partials) {
+  __shared__ float s_red[kLossThreads / 32][C * 4];
+  const int n = blockIdx.y;
+  const float* z = logits + static_cast<size_t>(n) * C * HW;
+  const long long* t = targets + static_cast<size_t>(n) * HW;
+  float acc[C][4];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[c][k] = 0.f;
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < HW;
+       r += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float p[C], lse;
+    softmax_px<C>(z, HW, r, p, lse);
+    const long long tv = __ldg(t + r);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const bool hit = (tv == c);
+      acc[c][0] += hit ? 1.f : 0.f;
+      acc[c][1] += hit ? (lse - __ldg(z + c * HW + r)) : 0.f;
+      acc[c][2] += hit ? p[c] : 0.f;
+      acc[c][3] += p[c];
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float w = warp_sum(acc[c][k]);
+      if (lane == 0) s_red[warp][c * 4 + k] = w;
+    }
+  __syncthreads();
+  if (threadIdx.x < C * 4) {
+    double s = 0.0;
+    for (int w = 0; w < kLossThreads / 32; ++w) s += static_cast<double>(s_red[w][threadIdx.x]);
+    partials[(static_cast<size_t>(n) * gridDim.x + blockIdx.x) * C * 4 + threadIdx.x] = s;
+  }
+}
+
+// stats[n][k][c] (k = cnt, ce, I, P) as fp32
+__global__ void seg_stats_finalize_kernel(const double* __restrict__ partials, int blocks, int N, int C,
+                                          float* stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C * 4) return;
+  const int n = i / (C * 4), r = i % (C * 4);
+  const int c = r / 4, k = r % 4;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += partials[(static_cast<size_t>(n) * blocks + b) * C * 4 + r];
+  stats[(static_cast<size_t>(n) * 4 + k) * C + c] = static_cast<float>(s);
+}
+
+// coef[n][3][C] = {dce, dI, dP} (already multiplied by the upstream gradient on the host side)
+template <int C>
+__global__ void __launch_bounds__(kLossThreads)
+seg_stats_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ targets,
+                     const float* __restrict__ coef, long long HW, float* __restrict__ dlogits) {
+  const int n = blockIdx.y;
+  const float* z = logits + static_cast<size_t>(n) * C * HW;
+  const long long* t = targets + static_cast<size_t>(n) * HW;
+  float* dz = dlogits + static_cast<size_t>(n) * C * HW;
+  float dce[C], dI[C], dP[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    dce[c] = __ldg(coef + (static_cast<size_t>(n) * 3 + 0) * C + c);
+    dI[c] = __ldg(coef + (static_cast<size_t>(n) * 3 + 1) * C + c);
+    dP[c] = __ldg(coef + (static_cast<size_t>(n) * 3 + 2) * C + c);
+  }
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < HW;
+       r += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float p[C], lse;
+    softmax_px<C>(z, HW, r, p, lse);
+    const long long tv = __ldg(t + r);
+    float wce = 0.f, gp = 0.f;
+    float g[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const bool hit = (tv == c);
+      if (hit) wce = dce[c];
+      g[c] = dP[c] + (hit ? dI[c] : 0.f);
+      gp = fmaf(g[c], p[c], gp);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float y = (tv == c) ? 1.f : 0.f;
+      dz[c * HW + r] = wce * (p[c] - y) + p[c] * (g[c] - gp);
+    }
+  }
+}
+
+template <int C>
+static int launch_stats(const float* logits, const long long* targets, int N, long long HW,
+                        double* partials, int blocks, float* stats, cudaStream_t s) {
+  seg_stats_kernel<C><<<dim3(blocks, N), kLossThreads, 0, s>>>(logits, targets, HW, partials);
+  seg_stats_finalize_kernel<<<(N * C * 4 + 127) / 128, 128, 0, s>>>(partials, blocks, N, C, stats);
+  return static_cast<int>(cudaGetLastError());
+}
+template <int C>
+static int launch_bwd(const float* logits, const long long* targets, const float* coef, int N,
+                      long long HW, float* dlogits, int blocks, cudaStream_t s) {
+  seg_stats_bwd_kernel<C><<<dim3(blocks, N), kLossThreads, 0, s>>>(logits, targets, coef, HW, dlogits);
+  return static_cast<int>(cudaGetLastError());
+}
+
+static int loss_blocks(int N, long long HW) {
+  long long per = (HW + kLossThreads * 4 - 1) / (kLossThreads * 4);
+  long long cap = (static_cast<long long>(num_sms()) * 8 + N - 1) / N;
+  if (per > cap) per = cap;
+  return static_cast<int>(per < 1 ? 1 : per);
+}
+
+}  // namespace ub2
+
+using namespace ub2;
+
+extern "C" {
+
+int ub2_seg_stats_blocks(int N, long long HW) { return loss_blocks(N, HW); }
+
+int ub2_seg_stats(const float* logits, const long long* targets, int N, int C, long long HW,
+                  double* partials, int blocks, float* stats, void* stream) {
+  if (N <= 0 || HW <= 0 || C < 1 || C > kLossMaxC) return UB2_ERR_SHAPE;
+  if (blocks != loss_blocks(N, HW)) return UB2_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (C) {
+    case 1: return launch_stats<1>(logits, targets, N, HW, partials, blocks, stats, s);
+    case 2: return launch_stats<2>(logits, targets, N, HW, partials, blocks, stats, s);
+    case 3: return launch_stats<3>(logits, targets, N, HW, partials, blocks, stats, s);
+    case 4: return launch_stats<4>(logits, targets, N, HW, partials, blocks, stats, s);
+    case 5: return launch_stats<5>(logits, targets, N, HW, partials, blocks, stats, s);
+    case 6: return launch_stats<6>(logits, targets, N, HW, partials, blocks, stats, s);
+    case 7: return launch_stats<7>(logits, targets, N, HW, partials, blocks, stats, s);
+    default: return launch_stats<8>(logits, targets, N, HW, partials, blocks, stats, s);
+  }
+}
+
+int ub2_seg_stats_bwd(const float* logits, const long long* targets, const float* coef, int N, int C,
+                      long long HW, float* dlogits, void* stream) {
+  if (N <= 0 || HW <= 0 || C < 1 || C > kLossMaxC) return UB2_ERR_SHAPE;
+  const int blocks = loss_blocks(N, HW);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (C) {
+    case 1: return launch_bwd<1>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 2: return launch_bwd<2>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 3: return launch_bwd<3>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 4: return launch_bwd<4>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 5: return launch_bwd<5>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 6: return launch_bwd<6>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 7: return launch_bwd<7>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    default: return launch_bwd<8>(logits, targets, coef, N, HW, dlogits, blocks, s);
+  }
+}
+
+}  // extern "C"

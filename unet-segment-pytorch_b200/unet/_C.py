@@ -68,10 +68,17 @@ def stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# kernels launched per entry point (default 1); used for the bench's `gpu_launches` claim
+_KERNELS_PER_CALL = {"ub2_conv_in_wgrad": 2, "ub2_outc_bwd": 2, "ub2_seg_stats": 2}
+LAUNCHES = 0
+
+
 def call(name: str, *args) -> None:
+    global LAUNCHES
     fn = getattr(lib(), name)
     fn.restype = ctypes.c_int
     check(fn(*args), name)
+    LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
 
 
 c_int = ctypes.c_int

@@ -1,8 +1,10 @@
 """Typed Python wrappers over the C ABI (one function per entry point family).
 
-All tensors are CUDA tensors; activations are NHWC bf16 ``(N, H, W, C)`` and
-must be contiguous in their last dimension.  These wrappers only allocate
-outputs / workspaces with torch and pass raw pointers through ctypes.
+All tensors are CUDA tensors; activations are NHWC bf16 ``(N, H, W, C)`` views
+that are dense in their last dimension.  These wrappers only allocate outputs /
+workspaces with torch and pass raw pointers through ctypes; nothing here
+computes on the host and nothing synchronises the device, so a whole training
+step can be captured into a CUDA graph.
 """
 from __future__ import annotations
 
@@ -12,18 +14,41 @@ from . import _C
 from ._C import byref, c_double, c_float, c_int, c_longlong, ptr, stream
 
 BF16 = torch.bfloat16
+F32 = torch.float32
+F64 = torch.float64
+
+_SMS = None
+# When set to a list, conv_fwd appends (start_event, end_event, algorithmic_flops) per launch.
+PROFILE = None
 
 
 def num_sms() -> int:
-    return int(_C.lib().ub2_num_sms())
+    global _SMS
+    if _SMS is None:
+        _SMS = int(_C.lib().ub2_num_sms())
+    return _SMS
 
 
 def _nhwc(t: torch.Tensor):
     assert t.dim() == 4 and t.dtype == BF16 and t.stride(3) == 1, "expected NHWC bf16"
     n, h, w, c = t.shape
-    ld = t.stride(2)
-    assert t.stride(1) == w * ld and t.stride(0) == h * w * ld, "expected dense NHWC rows"
+    ld = t.stride(2) if w > 1 else c
+    if h > 1:
+        assert t.stride(1) == w * ld, "expected dense NHWC rows"
+    if n > 1:
+        assert t.stride(0) == h * w * ld, "expected dense NHWC images"
     return n, h, w, c, ld
+
+
+def empty_nhwc(n, h, w, c, device):
+    return torch.empty((n, h, w, c), device=device, dtype=BF16)
+
+
+def _rows(name, *args) -> int:
+    r = int(getattr(_C.lib(), name)(*args))
+    if r <= 0:
+        _C.check(r if r < 0 else -1, name)
+    return r
 
 
 # --------------------------------------------------------------------------- convolution
@@ -42,7 +67,7 @@ def conv_fwd(x0, wgt, taps, x1=None, out=None, out1=None, split=0, scale=None, s
     cout = wgt.shape[0]
     assert wgt.dtype == BF16 and wgt.is_contiguous() and wgt.numel() == cout * taps * (c0 + c1)
     if out is None:
-        out = torch.empty((n, h, w, cout if out1 is None else split), device=x0.device, dtype=BF16)
+        out = empty_nhwc(n, h, w, cout if out1 is None else split, x0.device)
     _, _, _, _, ldo0 = _nhwc(out)
     ldo1 = 0
     if out1 is not None:
@@ -51,11 +76,18 @@ def conv_fwd(x0, wgt, taps, x1=None, out=None, out1=None, split=0, scale=None, s
     rows = 0
     if stats:
         rows = num_sms()
-        st = torch.empty((rows, 2, cout), device=x0.device, dtype=torch.float64)
+        st = torch.empty((rows, 2, cout), device=x0.device, dtype=F64)
     used = c_int(0)
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _C.call("ub2_conv_fwd", ptr(x0), ld0_in, c0, ptr(x1), ld1_in, c1, ptr(wgt), ptr(out), ldo0,
             ptr(out1), ldo1, split, n, h, w, cout, taps, ptr(scale), ptr(shift), int(relu),
             int(accumulate), ptr(st), rows, byref(used), bn_override, grid_override, stream())
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * n * h * w * cout * taps * (c0 + c1)))
     if stats:
         return out, st[: used.value]
     return out
@@ -70,9 +102,275 @@ def conv_wgrad(x0, dy, taps, x1=None, splits_override=0):
     n2, h2, w2, cout, ld_dy = _nhwc(dy)
     assert (n2, h2, w2) == (n, h, w)
     mtot = taps * (c0 + c1)
-    max_splits = max(1, min(2 * num_sms(), (64 << 20) // (mtot * cout * 4)))
-    partial = torch.empty((max_splits, mtot, cout), device=x0.device, dtype=torch.float32)
+    max_splits = max(1, min(2 * num_sms(), (96 << 20) // (mtot * cout * 4)))
+    partial = torch.empty((max_splits, mtot, cout), device=x0.device, dtype=F32)
     used = c_int(0)
     _C.call("ub2_conv_wgrad", ptr(x0), ld0_in, c0, ptr(x1), ld1_in, c1, ptr(dy), ld_dy,
             ptr(partial), max_splits, byref(used), n, h, w, cout, taps, splits_override, stream())
     return partial[: used.value]
+
+
+def wgrad_reduce(partial, cout, cin, taps, grad):
+    """grad (Cout,Cin,k,k) fp32 += sum over splits of partial (splits, taps*Cin, Cout)."""
+    assert grad.dtype == F32 and grad.is_contiguous() and partial.is_contiguous()
+    _C.call("ub2_wgrad_reduce", ptr(partial), partial.shape[0], cout, cin, taps, ptr(grad), stream())
+
+
+def pack_conv_weight(w, want_fwd=True, want_dgrad=True, out_scale=None):
+    """OIHW fp32 parameter -> (fwd pack (Cout,taps,Cin), dgrad pack (Cin,taps,Cout)) bf16."""
+    cout, cin, kh, kw = w.shape
+    taps = kh * kw
+    assert w.dtype == F32 and w.is_contiguous()
+    fwd = torch.empty((cout, taps, cin), device=w.device, dtype=BF16) if want_fwd else None
+    dg = torch.empty((cin, taps, cout), device=w.device, dtype=BF16) if want_dgrad else None
+    _C.call("ub2_pack_conv_weight", ptr(w), ptr(fwd), ptr(dg), cout, cin, taps, ptr(out_scale), stream())
+    return fwd, dg
+
+
+# --------------------------------------------------------------------------- batch norm
+def bn_finalize(partials, count, gamma, beta, running_mean, running_var, nbt, momentum, eps):
+    """Per-CTA sums -> (scale, shift, mean, invstd); updates the running buffers in place."""
+    rows, _, c = partials.shape
+    dev = partials.device
+    out = torch.empty((4, c), device=dev, dtype=F32)
+    _C.call("ub2_bn_finalize", ptr(partials), rows, c, c_double(float(count)), ptr(gamma), ptr(beta),
+            ptr(running_mean), ptr(running_var), ptr(nbt), c_float(momentum), c_float(eps),
+            ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), stream())
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps):
+    c = running_mean.numel()
+    out = torch.empty((2, c), device=running_mean.device, dtype=F32)
+    _C.call("ub2_bn_eval_coeffs", ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+            c_float(eps), c, ptr(out[0]), ptr(out[1]), stream())
+    return out[0], out[1]
+
+
+def bn_act(y, scale, shift, relu=True, pool=False, write_act=True):
+    """a = relu(scale*y+shift) (and its 2x2 max-pooled copy)."""
+    n, h, w, c, ld = _nhwc(y)
+    a = empty_nhwc(n, h, w, c, y.device) if write_act else None
+    p = empty_nhwc(n, h // 2, w // 2, c, y.device) if pool else None
+    _C.call("ub2_bn_act", ptr(y), ld, ptr(scale), ptr(shift), ptr(a), c, ptr(p), c, n, h, w, c,
+            int(relu), stream())
+    return a, p
+
+
+def bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, relu=True):
+    """BatchNorm(+ReLU, + max-pool routing) backward: returns (dy bf16, dgamma, dbeta)."""
+    n, h, w, c, ld_y = _nhwc(y)
+    ld_da = _nhwc(dA)[4] if dA is not None else 0
+    ld_dp = _nhwc(dP)[4] if dP is not None else 0
+    rows = _rows("ub2_bn_bwd_rows", n, h, w, c)
+    dev = y.device
+    partials = torch.empty((rows, 2, c), device=dev, dtype=F64)
+    _C.call("ub2_bn_bwd_reduce", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(y), ld_y, ptr(scale), ptr(shift),
+            ptr(mean), ptr(invstd), ptr(partials), rows, n, h, w, c, int(relu), stream())
+    grads = torch.zeros((2, c), device=dev, dtype=F32)
+    coef = torch.empty((3, c), device=dev, dtype=F32)
+    _C.call("ub2_bn_bwd_finalize", ptr(partials), rows, c, c_double(float(n * h * w)), ptr(gamma),
+            ptr(invstd), ptr(grads[0]), ptr(grads[1]), ptr(coef), stream())
+    dy = empty_nhwc(n, h, w, c, dev)
+    _C.call("ub2_bn_bwd_apply", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(y), ld_y, ptr(scale), ptr(shift),
+            ptr(mean), ptr(invstd), ptr(coef), ptr(dy), c, n, h, w, c, int(relu), stream())
+    return dy, grads[0], grads[1]
+
+
+# --------------------------------------------------------------------------- resampling
+def upsample(x, hu, wu, ho, wo):
+    n, hin, win, c, ld = _nhwc(x)
+    out = empty_nhwc(n, ho, wo, c, x.device)
+    _C.call("ub2_upsample_fwd", ptr(x), ld, ptr(out), c, n, hin, win, hu, wu, ho, wo, c, stream())
+    return out
+
+
+def upsample_bwd(dout, hin, win, hu, wu, into=None):
+    n, ho, wo, c, ld = _nhwc(dout)
+    acc = into is not None
+    din = into if acc else empty_nhwc(n, hin, win, c, dout.device)
+    _C.call("ub2_upsample_bwd", ptr(dout), ld, ptr(din), _nhwc(din)[4], int(acc), n, hin, win, hu, wu,
+            ho, wo, c, stream())
+    return din
+
+
+# --------------------------------------------------------------------------- attention gate
+def gate_rows(n, h, w, c):
+    return _rows("ub2_gate_rows", n, h, w, c)
+
+
+def gate_upstats(q, h, w):
+    n, hin, win, ci, ld = _nhwc(q)
+    rows = gate_rows(n, h, w, ci)
+    partials = torch.empty((rows, 2, ci), device=q.device, dtype=F64)
+    _C.call("ub2_gate_upstats", ptr(q), ld, n, hin, win, h, w, ci, ptr(partials), rows, stream())
+    return partials
+
+
+def gate_psi(q, xp, sg, hg, sx, hx, wpsi, stats=True):
+    n, hin, win, ci, ld_q = _nhwc(q)
+    _, h, w, _, ld_xp = _nhwc(xp)
+    psi = torch.empty((n, h, w), device=q.device, dtype=F32)
+    rows = gate_rows(n, h, w, ci)
+    partials = torch.empty((rows, 2, 1), device=q.device, dtype=F64) if stats else None
+    _C.call("ub2_gate_psi", ptr(q), ld_q, ptr(xp), ld_xp, ptr(sg), ptr(hg), ptr(sx), ptr(hx), ptr(wpsi),
+            ptr(psi), ptr(partials), rows, n, hin, win, h, w, ci, stream())
+    return psi, partials
+
+
+def gate_apply(psi, spsi, hpsi, x, save_a=True):
+    n, h, w, cx, ld = _nhwc(x)
+    out = empty_nhwc(n, h, w, cx, x.device)
+    a = torch.empty((n, h, w), device=x.device, dtype=F32) if save_a else None
+    _C.call("ub2_gate_apply", ptr(psi), ptr(spsi), ptr(hpsi), ptr(x), ld, ptr(out), cx, ptr(a), n, h, w,
+            cx, stream())
+    return out, a
+
+
+def gate_bwd_a(dout, x, a, psi, mean_psi, invstd_psi):
+    n, h, w, cx, ld_x = _nhwc(x)
+    ld_do = _nhwc(dout)[4]
+    dx = empty_nhwc(n, h, w, cx, x.device)
+    dpsin = torch.empty((n, h, w), device=x.device, dtype=F32)
+    rows = gate_rows(n, h, w, cx)
+    partials = torch.empty((rows, 2, 1), device=x.device, dtype=F64)
+    _C.call("ub2_gate_bwd_a", ptr(dout), ld_do, ptr(x), ld_x, ptr(a), ptr(psi), ptr(mean_psi),
+            ptr(invstd_psi), ptr(dx), cx, ptr(dpsin), ptr(partials), rows, n, h, w, cx, stream())
+    return dx, dpsin, partials
+
+
+def bn_bwd_finalize(partials, count, gamma, invstd):
+    rows, _, c = partials.shape
+    grads = torch.zeros((2, c), device=partials.device, dtype=F32)
+    coef = torch.empty((3, c), device=partials.device, dtype=F32)
+    _C.call("ub2_bn_bwd_finalize", ptr(partials), rows, c, c_double(float(count)), ptr(gamma),
+            ptr(invstd), ptr(grads[0]), ptr(grads[1]), ptr(coef), stream())
+    return grads[0], grads[1], coef
+
+
+def gate_bwd_s(dpsin, psi, coef_psi, mean_psi, invstd_psi, q, xp, sg, hg, sx, hx, mean_g, invstd_g,
+               mean_x, invstd_x, wpsi):
+    n, hin, win, ci, ld_q = _nhwc(q)
+    _, h, w, _, ld_xp = _nhwc(xp)
+    ds = empty_nhwc(n, h, w, ci, q.device)
+    rows = gate_rows(n, h, w, ci)
+    partials = torch.empty((rows, 4, ci), device=q.device, dtype=F64)
+    _C.call("ub2_gate_bwd_s", ptr(dpsin), ptr(psi), ptr(coef_psi), ptr(mean_psi), ptr(invstd_psi),
+            ptr(q), ld_q, ptr(xp), ld_xp, ptr(sg), ptr(hg), ptr(sx), ptr(hx), ptr(mean_g),
+            ptr(invstd_g), ptr(mean_x), ptr(invstd_x), ptr(wpsi), ptr(ds), ci, ptr(partials), rows, n,
+            hin, win, h, w, ci, stream())
+    return ds, partials
+
+
+def gate_bwd_finalize(partials, count, gamma_x, invstd_x, gamma_g, invstd_g):
+    rows, _, ci = partials.shape
+    grads = torch.zeros((5, ci), device=partials.device, dtype=F32)
+    coef = torch.empty((6, ci), device=partials.device, dtype=F32)
+    _C.call("ub2_gate_bwd_finalize", ptr(partials), rows, ci, c_double(float(count)), ptr(gamma_x),
+            ptr(invstd_x), ptr(gamma_g), ptr(invstd_g), ptr(grads[0]), ptr(grads[1]), ptr(grads[2]),
+            ptr(grads[3]), ptr(grads[4]), ptr(coef), stream())
+    # dgamma_x, dbeta_x, dgamma_g, dbeta_g, dwpsi
+    return grads, coef
+
+
+def gate_bwd_xg(ds, xp, q, mean_x, invstd_x, mean_g, invstd_g, coef):
+    n, hin, win, ci, ld_q = _nhwc(q)
+    _, h, w, _, ld_xp = _nhwc(xp)
+    dxp = empty_nhwc(n, h, w, ci, q.device)
+    dgup = empty_nhwc(n, h, w, ci, q.device)
+    _C.call("ub2_gate_bwd_xg", ptr(ds), _nhwc(ds)[4], ptr(xp), ld_xp, ptr(q), ld_q, ptr(mean_x),
+            ptr(invstd_x), ptr(mean_g), ptr(invstd_g), ptr(coef), ptr(dxp), ci, ptr(dgup), ci, n, hin,
+            win, h, w, ci, stream())
+    return dxp, dgup
+
+
+# --------------------------------------------------------------------------- network ends
+def conv_in_fwd(x, w, stats=True):
+    """First conv: x (N,Cin,H,W) fp32 NCHW, w (Cout,Cin,3,3) fp32 -> NHWC bf16 (+ stat rows)."""
+    assert x.dtype == F32 and x.is_contiguous() and w.dtype == F32 and w.is_contiguous()
+    n, cin, h, wd = x.shape
+    cout = w.shape[0]
+    y = empty_nhwc(n, h, wd, cout, x.device)
+    rows = _rows("ub2_conv_in_rows", n, h, wd, cout)
+    partials = torch.empty((rows, 2, cout), device=x.device, dtype=F64) if stats else None
+    _C.call("ub2_conv_in_fwd", ptr(x), ptr(w), ptr(y), cout, ptr(partials), rows, n, cin, h, wd, cout,
+            stream())
+    return y, partials
+
+
+def conv_in_wgrad(x, dy, cout):
+    n, cin, h, wd = x.shape
+    rows = _rows("ub2_conv_in_rows", n, h, wd, cout)
+    partials = torch.empty((rows, cin, 9, cout), device=x.device, dtype=F64)
+    grad = torch.zeros((cout, cin, 3, 3), device=x.device, dtype=F32)
+    _C.call("ub2_conv_in_wgrad", ptr(x), ptr(dy), _nhwc(dy)[4], ptr(partials), rows, ptr(grad), n, cin,
+            h, wd, cout, stream())
+    return grad
+
+
+def outc_fwd(a, w, bias):
+    n, h, wd, c, ld = _nhwc(a)
+    k = w.shape[0]
+    logits = torch.empty((n, k, h, wd), device=a.device, dtype=F32)
+    _C.call("ub2_outc_fwd", ptr(a), ld, ptr(w), ptr(bias), ptr(logits), n, h, wd, c, k, stream())
+    return logits
+
+
+def outc_bwd(dlogits, a, w, need_da=True):
+    n, h, wd, c, ld = _nhwc(a)
+    k = w.shape[0]
+    assert dlogits.dtype == F32 and dlogits.is_contiguous()
+    rows = _rows("ub2_outc_rows", n, h, wd, c)
+    partials = torch.empty((rows, k * c + k), device=a.device, dtype=F64)
+    da = empty_nhwc(n, h, wd, c, a.device) if need_da else None
+    dw = torch.zeros((k, c, 1, 1), device=a.device, dtype=F32)
+    db = torch.zeros((k,), device=a.device, dtype=F32)
+    _C.call("ub2_outc_bwd", ptr(dlogits), ptr(a), ld, ptr(w), ptr(da), c, ptr(partials), rows, ptr(dw),
+            ptr(db), n, h, wd, c, k, stream())
+    return da, dw, db
+
+
+# --------------------------------------------------------------------------- loss / metrics
+def seg_stats(logits, targets):
+    """(N,4,C) fp32: per image and class {count, CE sum, intersection, prob sum}."""
+    assert logits.dtype == F32 and logits.is_contiguous() and targets.dtype == torch.int64
+    n, c, h, w = logits.shape
+    targets = targets.contiguous()
+    blocks = _rows("ub2_seg_stats_blocks", n, c_longlong(h * w))
+    partials = torch.empty((n, blocks, c, 4), device=logits.device, dtype=F64)
+    stats = torch.empty((n, 4, c), device=logits.device, dtype=F32)
+    _C.call("ub2_seg_stats", ptr(logits), ptr(targets), n, c, c_longlong(h * w), ptr(partials), blocks,
+            ptr(stats), stream())
+    return stats
+
+
+def seg_stats_bwd(logits, targets, coef):
+    """coef (N,3,C) fp32 = {dL/dCE, dL/dI, dL/dP}; returns dL/dlogits (N,C,H,W) fp32."""
+    n, c, h, w = logits.shape
+    coef = coef.contiguous()
+    assert coef.dtype == F32 and coef.shape == (n, 3, c)
+    dl = torch.empty_like(logits)
+    _C.call("ub2_seg_stats_bwd", ptr(logits), ptr(targets.contiguous()), ptr(coef), n, c,
+            c_longlong(h * w), ptr(dl), stream())
+    return dl
+
+
+def confusion(pred, target, num_classes, cm, ignore_index=None, threshold=None, mask_out=None):
+    """cm ((C+1),(C+1)) int64 += histogram of (target, prediction)."""
+    target = target.contiguous()
+    assert target.dtype == torch.int64 and cm.dtype == torch.int64 and cm.is_contiguous()
+    if pred.dim() == 4:
+        assert pred.dtype == F32 and pred.is_contiguous()
+        n, c, h, w = pred.shape
+        assert c == num_classes
+        mode = 2 if threshold is not None else 0
+    else:
+        pred = pred.contiguous()
+        assert pred.dtype == torch.int64
+        n, h, w = pred.shape
+        mode = 1
+    _C.call("ub2_confusion", ptr(pred), ptr(target), mode, n, num_classes, c_longlong(h * w),
+            c_longlong(ignore_index if ignore_index is not None else 0),
+            int(ignore_index is not None), c_float(threshold if threshold is not None else 0.5), ptr(cm),
+            ptr(mask_out), stream())
+    return cm

@@ -1,0 +1,359 @@
+"""Autograd glue: each fused block of the network is one ``torch.autograd.Function``
+whose forward and backward are sequences of C-ABI kernel launches (``kernels.py``).
+
+Tensors crossing these functions are *logical NCHW, channels_last, bf16* — i.e.
+physically NHWC bf16, the layout every kernel reads — so chaining blocks never
+copies or transposes.  Parameters stay fp32 in the reference's layout and their
+gradients are returned as fp32 tensors of the same shape.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels as K
+
+BF16 = torch.bfloat16
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW tensor -> dense NHWC bf16 view (no copy if already channels_last bf16)."""
+    if not x.is_cuda:
+        raise RuntimeError("unet-b200 modules run on CUDA tensors only (no CPU fallback); "
+                           "move the model and its inputs to a B200 with .to('cuda')")
+    if x.dtype != BF16:
+        x = x.to(BF16)
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def from_nhwc(t: torch.Tensor) -> torch.Tensor:
+    return t.permute(0, 3, 1, 2)
+
+
+def _bn_train_coeffs(partials, count, bn):
+    """Batch statistics -> (scale, shift, mean, invstd); running buffers updated like
+    nn.BatchNorm2d in train mode (layers.py:33)."""
+    if bn.momentum is None:
+        raise NotImplementedError("BatchNorm momentum=None (cumulative average) is not supported")
+    track = bn.track_running_stats and bn.running_mean is not None
+    return K.bn_finalize(partials, count, bn.weight, bn.bias,
+                         bn.running_mean if track else None, bn.running_var if track else None,
+                         bn.num_batches_tracked if track else None, float(bn.momentum), float(bn.eps))
+
+
+def _bn_frozen_coeffs(bn):
+    """Eval mode: normalise with the running statistics."""
+    scale, shift = K.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps))
+    invstd = torch.rsqrt(bn.running_var + bn.eps)
+    return scale, shift, bn.running_mean, invstd
+
+
+def _use_batch_stats(bn) -> bool:
+    return bn.training or bn.running_mean is None
+
+
+class ConvBnRelu(torch.autograd.Function):
+    """conv3x3(pad 1, no bias) over one or two (virtually concatenated) inputs -> BatchNorm ->
+    ReLU, optionally also returning the 2x2 max-pooled activation (DoubleConv / Down / the
+    concat in Up, layers.py:31-38, :56, :105)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, gamma, beta, bn, pool):
+        a0 = to_nhwc(x0)
+        a1 = to_nhwc(x1) if x1 is not None else None
+        n, h, w, _ = a0.shape
+        taps = weight.shape[2] * weight.shape[3]
+        need_grad = any(ctx.needs_input_grad)
+        need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        wf, wd = K.pack_conv_weight(weight, True, need_dx)
+        batch = _use_batch_stats(bn)
+        if not batch and not need_grad:
+            # inference: BatchNorm folded into the conv epilogue, ReLU fused
+            scale, shift = K.bn_eval_coeffs(gamma, beta, bn.running_mean, bn.running_var, float(bn.eps))
+            a = K.conv_fwd(a0, wf, taps, x1=a1, scale=scale, shift=shift, relu=True)
+            p = K.bn_act(a, None, None, relu=False, pool=True, write_act=False)[1] if pool else None
+            return from_nhwc(a), (from_nhwc(p) if pool else None)
+        if batch:
+            y, st = K.conv_fwd(a0, wf, taps, x1=a1, stats=True)
+            scale, shift, mean, invstd = _bn_train_coeffs(st, n * h * w, bn)
+        else:
+            y = K.conv_fwd(a0, wf, taps, x1=a1)
+            scale, shift, mean, invstd = _bn_frozen_coeffs(bn)
+        a, p = K.bn_act(y, scale, shift, relu=True, pool=pool)
+        ctx.save_for_backward(a0, a1, y, scale, shift, mean, invstd, gamma, wd)
+        ctx.meta = (weight.shape, batch)
+        return from_nhwc(a), (from_nhwc(p) if pool else None)
+
+    @staticmethod
+    def backward(ctx, dA, dP):
+        a0, a1, y, scale, shift, mean, invstd, gamma, wd = ctx.saved_tensors
+        wshape, batch = ctx.meta
+        cout, cin, kh, kw = wshape
+        taps = kh * kw
+        dA_n = to_nhwc(dA) if dA is not None else None
+        dP_n = to_nhwc(dP) if dP is not None else None
+        dy, dgamma, dbeta = _bn_backward(dA_n, dP_n, y, scale, shift, mean, invstd, gamma, batch)
+        gw = None
+        if ctx.needs_input_grad[2]:
+            part = K.conv_wgrad(a0, dy, taps, x1=a1)
+            gw = torch.zeros(wshape, device=dy.device, dtype=torch.float32)
+            K.wgrad_reduce(part, cout, cin, taps, gw)
+        d0 = d1 = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            n, h, w, _ = a0.shape
+            c0 = a0.shape[3]
+            d0 = K.empty_nhwc(n, h, w, c0, dy.device)
+            d1 = K.empty_nhwc(n, h, w, a1.shape[3], dy.device) if a1 is not None else None
+            K.conv_fwd(dy, wd, taps, out=d0, out1=d1, split=c0)
+            d0 = from_nhwc(d0)
+            d1 = from_nhwc(d1) if d1 is not None else None
+        return d0, d1, gw, dgamma, dbeta, None, None
+
+
+def _bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, batch, relu=True):
+    n, h, w, c = y.shape
+    if batch:
+        return K.bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, relu=relu)
+    # frozen statistics (eval-mode backward): dy = dz * gamma * invstd, no mean terms
+    ld = lambda t: K._nhwc(t)[4] if t is not None else 0
+    rows = K._rows("ub2_bn_bwd_rows", n, h, w, c)
+    partials = torch.empty((rows, 2, c), device=y.device, dtype=torch.float64)
+    K._C.call("ub2_bn_bwd_reduce", K.ptr(dA), ld(dA), K.ptr(dP), ld(dP), K.ptr(y), ld(y), K.ptr(scale),
+              K.ptr(shift), K.ptr(mean), K.ptr(invstd), K.ptr(partials), rows, n, h, w, c, int(relu),
+              K.stream())
+    dgamma, dbeta, coef = K.bn_bwd_finalize(partials, n * h * w, gamma, invstd)
+    coef[1:].zero_()
+    dy = K.empty_nhwc(n, h, w, c, y.device)
+    K._C.call("ub2_bn_bwd_apply", K.ptr(dA), ld(dA), K.ptr(dP), ld(dP), K.ptr(y), ld(y), K.ptr(scale),
+              K.ptr(shift), K.ptr(mean), K.ptr(invstd), K.ptr(coef), K.ptr(dy), c, n, h, w, c, int(relu),
+              K.stream())
+    return dy, dgamma, dbeta
+
+
+class ConvInBnRelu(torch.autograd.Function):
+    """First stage: conv3x3 on the fp32 NCHW network input (Cin = n_channels) -> BN -> ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, bn):
+        if not x.is_cuda:
+            raise RuntimeError("unet-b200 modules run on CUDA tensors only (no CPU fallback)")
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("gradient w.r.t. the network input is not implemented")
+        x = x.contiguous().float()
+        n, _, h, w = x.shape
+        batch = _use_batch_stats(bn)
+        y, st = K.conv_in_fwd(x, weight, stats=batch)
+        if batch:
+            scale, shift, mean, invstd = _bn_train_coeffs(st, n * h * w, bn)
+        else:
+            scale, shift, mean, invstd = _bn_frozen_coeffs(bn)
+        a, _ = K.bn_act(y, scale, shift, relu=True, pool=False)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, y, scale, shift, mean, invstd, gamma)
+            ctx.meta = (weight.shape, batch)
+        return from_nhwc(a)
+
+    @staticmethod
+    def backward(ctx, dA):
+        x, y, scale, shift, mean, invstd, gamma = ctx.saved_tensors
+        wshape, batch = ctx.meta
+        dy, dgamma, dbeta = _bn_backward(to_nhwc(dA), None, y, scale, shift, mean, invstd, gamma, batch)
+        gw = K.conv_in_wgrad(x, dy, wshape[0])
+        return None, gw, dgamma, dbeta, None
+
+
+class Upsample2x(torch.autograd.Function):
+    """nn.Upsample(2x, bilinear, align_corners=True) + F.pad to the skip size (layers.py:78,
+    :98-102)."""
+
+    @staticmethod
+    def forward(ctx, x, out_h, out_w):
+        a = to_nhwc(x)
+        n, h, w, c = a.shape
+        ctx.geom = (h, w, 2 * h, 2 * w)
+        return from_nhwc(K.upsample(a, 2 * h, 2 * w, out_h, out_w))
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, w, hu, wu = ctx.geom
+        return from_nhwc(K.upsample_bwd(to_nhwc(dout), h, w, hu, wu)), None, None
+
+
+class AttentionGateFn(torch.autograd.Function):
+    """AttentionGate.forward (layers.py:171-192) as two tensor-core 1x1 projections plus three
+    bandwidth-bound passes; see csrc/gate.cu."""
+
+    @staticmethod
+    def forward(ctx, g, x, w_g, w_x, w_psi, gam_g, bet_g, gam_x, bet_x, gam_p, bet_p, bn_g, bn_x, bn_p):
+        gn, xn = to_nhwc(g), to_nhwc(x)
+        n, h, w, cx = xn.shape
+        count = n * h * w
+        need_grad = any(ctx.needs_input_grad)
+        wgf, wgd = K.pack_conv_weight(w_g, True, need_grad)
+        wxf, wxd = K.pack_conv_weight(w_x, True, need_grad)
+        wpsi = w_psi.reshape(-1)
+        batch = _use_batch_stats(bn_x)
+        q = K.conv_fwd(gn, wgf, 1)
+        if batch:
+            xp, st_x = K.conv_fwd(xn, wxf, 1, stats=True)
+            sg, hg, mg, ig = _bn_train_coeffs(K.gate_upstats(q, h, w), count, bn_g)
+            sx, hx, mx, ix = _bn_train_coeffs(st_x, count, bn_x)
+        else:
+            xp = K.conv_fwd(xn, wxf, 1)
+            sg, hg, mg, ig = _bn_frozen_coeffs(bn_g)
+            sx, hx, mx, ix = _bn_frozen_coeffs(bn_x)
+        psi, st_p = K.gate_psi(q, xp, sg, hg, sx, hx, wpsi, stats=batch)
+        if batch:
+            sp, hp, mp, ip = _bn_train_coeffs(st_p, count, bn_p)
+        else:
+            sp, hp, mp, ip = _bn_frozen_coeffs(bn_p)
+        out, a = K.gate_apply(psi, sp, hp, xn, save_a=need_grad)
+        if need_grad:
+            ctx.save_for_backward(gn, xn, q, xp, psi, a, sg, hg, mg, ig, sx, hx, mx, ix, mp, ip, wgd, wxd,
+                                  wpsi, gam_g, gam_x, gam_p)
+            ctx.meta = (w_g.shape, w_x.shape, w_psi.shape, batch)
+        return from_nhwc(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (gn, xn, q, xp, psi, a, sg, hg, mg, ig, sx, hx, mx, ix, mp, ip, wgd, wxd, wpsi, gam_g, gam_x,
+         gam_p) = ctx.saved_tensors
+        sh_g, sh_x, sh_p, batch = ctx.meta
+        n, h, w, cx = xn.shape
+        _, hin, win, cg = gn.shape
+        ci = q.shape[3]
+        count = n * h * w
+        d = to_nhwc(dout)
+        dx, dpsin, part = K.gate_bwd_a(d, xn, a, psi, mp, ip)
+        dgam_p, dbet_p, coef_p = K.bn_bwd_finalize(part, count, gam_p, ip)
+        if not batch:
+            coef_p[1:].zero_()
+        ds, part2 = K.gate_bwd_s(dpsin, psi, coef_p, mp, ip, q, xp, sg, hg, sx, hx, mg, ig, mx, ix, wpsi)
+        grads, coef = K.gate_bwd_finalize(part2, count, gam_x, ix, gam_g, ig)
+        if not batch:
+            coef[1:3].zero_()
+            coef[4:6].zero_()
+        dxp, dgup = K.gate_bwd_xg(ds, xp, q, mx, ix, mg, ig, coef)
+        dq = K.upsample_bwd(dgup, hin, win, h, w)
+        gw_x = torch.zeros(sh_x, device=d.device, dtype=torch.float32)
+        K.wgrad_reduce(K.conv_wgrad(xn, dxp, 1), ci, cx, 1, gw_x)
+        gw_g = torch.zeros(sh_g, device=d.device, dtype=torch.float32)
+        K.wgrad_reduce(K.conv_wgrad(gn, dq, 1), ci, cg, 1, gw_g)
+        K.conv_fwd(dxp, wxd, 1, out=dx, accumulate=True)
+        dg = K.conv_fwd(dq, wgd, 1)
+        return (from_nhwc(dg), from_nhwc(dx), gw_g, gw_x, grads[4].reshape(sh_p), grads[2], grads[3],
+                grads[0], grads[1], dgam_p, dbet_p, None, None, None)
+
+
+class OutConvFn(torch.autograd.Function):
+    """OutConv: 1x1 conv with bias to fp32 NCHW logits (layers.py:120-123)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        a = to_nhwc(x)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(a, weight)
+        return K.outc_fwd(a, weight.reshape(weight.shape[0], -1), bias)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        a, weight = ctx.saved_tensors
+        da, dw, db = K.outc_bwd(dlogits.contiguous().float(), a, weight.reshape(weight.shape[0], -1),
+                                need_da=ctx.needs_input_grad[0])
+        return (from_nhwc(da) if da is not None else None), dw.reshape(weight.shape), db
+
+
+class SegStats(torch.autograd.Function):
+    """Per-(image, class) pixel sums every reference loss is built from; see csrc/loss.cu.
+    Returns (count, ce_sum, intersection, prob_sum), each (N, C) fp32."""
+
+    @staticmethod
+    def forward(ctx, logits, targets):
+        if not logits.is_cuda:
+            raise RuntimeError("unet-b200 losses run on CUDA tensors only (no CPU fallback)")
+        logits = logits.contiguous().float()
+        st = K.seg_stats(logits, targets)
+        ctx.save_for_backward(logits, targets)
+        cnt, ce, inter, psum = st.unbind(dim=1)
+        ctx.mark_non_differentiable(cnt)
+        return cnt, ce, inter, psum
+
+    @staticmethod
+    def backward(ctx, _dcnt, dce, dinter, dpsum):
+        logits, targets = ctx.saved_tensors
+        z = lambda t: t if t is not None else torch.zeros(logits.shape[:2], device=logits.device)
+        coef = torch.stack([z(dce), z(dinter), z(dpsum)], dim=1).float()
+        return K.seg_stats_bwd(logits, targets, coef), None
+
+
+class MaxPool2x2(torch.autograd.Function):
+    """Standalone nn.MaxPool2d(2) (layers.py:56) for `Down` used outside the fused network."""
+
+    @staticmethod
+    def forward(ctx, x):
+        a = to_nhwc(x)
+        ctx.save_for_backward(a)
+        return from_nhwc(K.bn_act(a, None, None, relu=False, pool=True, write_act=False)[1])
+
+    @staticmethod
+    def backward(ctx, dp):
+        (a,) = ctx.saved_tensors
+        n, h, w, c = a.shape
+        dev = a.device
+        one = torch.ones(c, device=dev)
+        zero = torch.zeros(c, device=dev)
+        coef = torch.cat([one, zero, zero]).contiguous()
+        dpn = to_nhwc(dp)
+        dy = K.empty_nhwc(n, h, w, c, dev)
+        K._C.call("ub2_bn_bwd_apply", K.ptr(None), 0, K.ptr(dpn), K._nhwc(dpn)[4], K.ptr(a), K._nhwc(a)[4],
+                  K.ptr(one), K.ptr(zero), K.ptr(zero), K.ptr(one), K.ptr(coef), K.ptr(dy), c, n, h, w, c, 0,
+                  K.stream())
+        return from_nhwc(dy)
+
+
+class ConvFn(torch.autograd.Function):
+    """Plain convolution (no BN): weight is any (Cout, Cin, k, k) fp32 tensor, k in {1, 3};
+    optional per-output-channel bias added to the fp32 accumulator in the epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        a = to_nhwc(x)
+        weight = weight.contiguous()
+        taps = weight.shape[2] * weight.shape[3]
+        wf, wd = K.pack_conv_weight(weight, True, ctx.needs_input_grad[0])
+        ctx.save_for_backward(a, wd)
+        ctx.meta = weight.shape
+        if bias is None:
+            return from_nhwc(K.conv_fwd(a, wf, taps))
+        bias = bias.contiguous().float()
+        return from_nhwc(K.conv_fwd(a, wf, taps, scale=torch.ones_like(bias), shift=bias))
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, wd = ctx.saved_tensors
+        cout, cin, kh, kw = ctx.meta
+        taps = kh * kw
+        d = to_nhwc(dy)
+        gw = gb = None
+        if ctx.needs_input_grad[1]:
+            gw = torch.zeros(ctx.meta, device=d.device, dtype=torch.float32)
+            K.wgrad_reduce(K.conv_wgrad(a, d, taps), cout, cin, taps, gw)
+        if ctx.needs_input_grad[2]:
+            gb = d.float().sum(dim=(0, 1, 2))
+        dx = from_nhwc(K.conv_fwd(d, wd, taps)) if ctx.needs_input_grad[0] else None
+        return dx, gw, gb
+
+
+def conv_transpose2x2(x, weight, bias, out_h, out_w):
+    """nn.ConvTranspose2d(C, C/2, kernel_size=2, stride=2) + F.pad to the skip size
+    (layers.py:81, :98-102).  Because kernel == stride the output pixels do not overlap: it is a
+    1x1 convolution to 4*Cout channels (on the tensor cores) followed by a pixel shuffle."""
+    cin, cout = weight.shape[0], weight.shape[1]
+    n, _, h, w = x.shape
+    w1 = weight.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)      # row = (i, j, co)
+    y = ConvFn.apply(x, w1, bias.repeat(4))                            # (N, 4*Cout, h, w) channels_last
+    y = y.permute(0, 2, 3, 1).reshape(n, h, w, 2, 2, cout)
+    y = y.permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * h, 2 * w, cout).permute(0, 3, 1, 2)
+    dy, dx = out_h - 2 * h, out_w - 2 * w
+    if dy or dx:
+        y = torch.nn.functional.pad(y, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    return y.contiguous(memory_format=torch.channels_last)

@@ -1,0 +1,133 @@
+"""Batch-sharded data-parallel training step — the B200 form of the reference's
+gradient-accumulation loop (scripts/train.py:103-161).
+
+The reference reaches its effective batch by running ``accumulation_steps`` micro-batches one
+after another on one device: each micro-batch has its own BatchNorm batch statistics, its loss
+is divided by ``accumulation_steps`` (train.py:133), gradients sum into ``.grad`` and one
+clip + optimizer step follows (train.py:139-143).  Here the micro-batches run at the same time,
+one per GPU (one process per GPU): rank r computes forward/backward on its shard with the loss
+divided by ``world_size``, gradients are summed with NCCL all-reduce over NVLink, and every
+rank then applies the identical clip + optimizer step.  Up to summation order this is the same
+arithmetic (no SyncBN: statistics stay per micro-batch, exactly as in the reference).
+
+Gradients live in a few flat fp32 buckets cut in backward order; a bucket's all-reduce is
+launched from an autograd hook as soon as its last gradient has been accumulated, on NCCL's
+own stream, so communication overlaps the rest of backward.  With ``world_size == 1`` the same
+code runs without collectives.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class _Bucket:
+    __slots__ = ("flat", "params", "pending", "work")
+
+    def __init__(self, flat, params):
+        self.flat, self.params, self.pending, self.work = flat, params, 0, None
+
+
+class BatchShardedTrainer:
+    """fwd + loss/world + bwd (+ overlapped gradient all-reduce) + clip + optimizer step.
+
+    Parameters
+    ----------
+    model, criterion, optimizer : as built by the reference's train.py (:306-350)
+    grad_clip : max gradient norm (train.py:141), 0 disables
+    bucket_mb : flat gradient bucket size
+    process_group : None -> default group if torch.distributed is initialised
+    """
+
+    def __init__(self, model, criterion, optimizer, grad_clip: float = 0.0, bucket_mb: float = 24.0,
+                 process_group=None):
+        self.model, self.criterion, self.optimizer, self.grad_clip = model, criterion, optimizer, grad_clip
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.buckets: List[_Bucket] = []
+        self._build_buckets(bucket_mb)
+        self._loss_acc: Optional[torch.Tensor] = None
+        self._steps = 0
+
+    # ------------------------------------------------------------------ flat gradient buckets
+    def _build_buckets(self, bucket_mb: float) -> None:
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        limit = int(bucket_mb * (1 << 20) / 4)
+        groups, cur, cur_n = [], [], 0
+        for p in reversed(params):  # backward produces gradients roughly in reverse registration order
+            cur.append(p)
+            cur_n += p.numel()
+            if cur_n >= limit:
+                groups.append(cur)
+                cur, cur_n = [], 0
+        if cur:
+            groups.append(cur)
+        for g in groups:
+            flat = torch.zeros(sum(p.numel() for p in g), device=g[0].device, dtype=torch.float32)
+            off = 0
+            for p in g:
+                p.grad = flat[off:off + p.numel()].view_as(p)  # autograd accumulates in place into the view
+                off += p.numel()
+            b = _Bucket(flat, g)
+            self.buckets.append(b)
+            if self.world > 1:
+                for p in g:
+                    p.register_post_accumulate_grad_hook(self._make_hook(b))
+
+    def _make_hook(self, bucket: _Bucket):
+        def hook(_param):
+            bucket.pending -= 1
+            if bucket.pending == 0:
+                bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return hook
+
+    # ------------------------------------------------------------------ one optimizer step
+    def step(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        """One micro-batch per rank and one optimizer step.  ``images`` / ``masks`` may be host
+        (pinned) tensors: they are copied to this rank's GPU asynchronously.  Returns the
+        un-divided micro-batch loss as a 0-dim device tensor (no host sync)."""
+        dev = next(self.model.parameters()).device
+        images = images.to(dev, non_blocking=True)
+        masks = masks.to(dev, non_blocking=True)
+        self.model.train()
+        for b in self.buckets:
+            b.flat.zero_()
+            b.pending = len(b.params)
+            b.work = None
+        outputs = self.model(images)
+        loss = self.criterion(outputs, masks)
+        (loss / self.world).backward()
+        if self.world > 1:
+            for b in self.buckets:
+                if b.work is None:  # a parameter without gradient this step
+                    b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            for b in self.buckets:
+                b.work.wait()
+        if self.grad_clip > 0:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip, foreach=True)
+        self.optimizer.step()
+        self._steps += 1
+        return loss.detach()
+
+    @torch.no_grad()
+    def evaluate(self, images: torch.Tensor, masks: torch.Tensor, metrics=None) -> torch.Tensor:
+        """validate() of the reference (train.py:164-197) for one batch: eval-mode forward
+        (BatchNorm folded, ReLU fused), loss, and device-side confusion-matrix update."""
+        dev = next(self.model.parameters()).device
+        images = images.to(dev, non_blocking=True)
+        masks = masks.to(dev, non_blocking=True)
+        self.model.eval()
+        out = self.model(images)
+        if metrics is not None:
+            metrics.update(out, masks)
+        return self.criterion(out, masks)
+
+    def all_reduce_confusion(self, metrics) -> None:
+        """Confusion matrices are additive over shards: sum them across ranks."""
+        if self.world == 1:
+            return
+        cm = torch.from_numpy(metrics.confusion_matrix.copy()).to(next(self.model.parameters()).device)
+        dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=self.group)
+        metrics.confusion_matrix = cm.cpu().numpy()
