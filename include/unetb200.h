@@ -1,18 +1,21 @@
 /* libunetb200 — C ABI of the B200 (sm_100a) Attention U-Net hot path.
  *
  * Boundary contract:
- *  - plain pointers and sizes only, no torch / C++ types; every entry point returns
- *    0 on success, a positive cudaError_t, or a negative UB2_ERR_* code; no exception
- *    crosses the boundary;
- *  - the library never allocates, frees or retains device memory: activations, grads,
- *    statistics and workspaces are owned by the caller (torch's allocator);
- *  - every call is asynchronous on the passed cudaStream_t (as void*), never
- *    synchronises the device, and is re-entrant (autograd calls backward entry points
- *    from its own thread);
- *  - activations are NHWC bf16 ("(N,H,W,C), channel stride ld"), parameters stay in the
- *    reference's fp32 OIHW layout and are packed to bf16 by ub2_pack_conv_weight.
+ *  - plain pointers and sizes only, no torch / C++ types; every entry point returns 0 on
+ *    success, a positive cudaError_t, or a negative UB2_ERR_* code (the *_rows / *_blocks
+ *    queries return a positive count instead); no exception crosses the boundary;
+ *  - the library never allocates, frees or retains device memory: activations, gradients,
+ *    statistics and workspaces are owned by the caller (torch's caching allocator);
+ *  - every call is asynchronous on the passed cudaStream_t (as void*), never synchronises
+ *    the device and is re-entrant (autograd calls the backward entry points from its own
+ *    thread); a whole training step can therefore be captured into a CUDA graph;
+ *  - activations are NHWC bf16 "(N,H,W,C), channel stride ld" (ld in elements, multiple of 8,
+ *    base pointers 16-byte aligned); parameters stay in the reference's fp32 OIHW layout and
+ *    are packed to bf16 by ub2_pack_conv_weight; per-channel vectors are fp32;
+ *  - reductions are deterministic: kernels write per-block partial rows (doubles), a finalize
+ *    kernel sums them in a fixed order.
  *
- * Each entry point cites the reference code (paths relative to the reference repo)
+ * Each entry point cites the reference code (paths relative to the reference repository)
  * whose work it replaces.
  */
 #ifndef UNETB200_H
@@ -25,26 +28,27 @@ extern "C" {
 #endif
 
 #define UB2_OK 0
-#define UB2_ERR_SHAPE (-1)
-#define UB2_ERR_ALIGN (-2)
-#define UB2_ERR_WORKSPACE (-3)
-#define UB2_ERR_DRIVER (-4)
-#define UB2_ERR_ARCH (-5)
+#define UB2_ERR_SHAPE (-1)     /* unsupported shape */
+#define UB2_ERR_ALIGN (-2)     /* pointer / stride alignment */
+#define UB2_ERR_WORKSPACE (-3) /* workspace rows do not match the *_rows query */
+#define UB2_ERR_DRIVER (-4)    /* cuTensorMapEncodeTiled unavailable / failed */
+#define UB2_ERR_ARCH (-5)      /* not an sm_100 device */
 
 int ub2_version(void);
 int ub2_num_sms(void);
 
-/* ---- convolution on tcgen05 tensor cores ------------------------------------------------
- * ub2_conv_fwd: nn.Conv2d(k=3,p=1,bias=False) of DoubleConv (unet/models/layers.py:32,35)
- * and the 1x1 projections of AttentionGate (layers.py:152,158) as an NHWC bf16 implicit
- * GEMM.  The input channel axis may span two tensors (in0: C0 channels, in1: C1 channels):
- * this is torch.cat([x2, x1], dim=1) of Up/AttentionUp (layers.py:105, :254) without the
- * copy.  wgt is (Cout, taps, C0+C1) bf16.  Optional epilogue: per-channel scale/shift
- * (BatchNorm folded, layers.py:33 in eval mode), ReLU (layers.py:34), accumulate into the
- * destination, split of the output channels over two tensors (the dgrad of a concat), and
- * per-CTA per-channel sum / sum-of-squares rows (stats: (stats_rows,2,Cout) doubles) for
- * train-mode BatchNorm statistics.  Called with the flipped/transposed weight pack it is
- * the data-gradient pass autograd runs for the same nn.Conv2d.
+/* ======================= convolutions on tcgen05 tensor cores =========================== */
+
+/* nn.Conv2d(k=3,p=1,bias=False) of DoubleConv (unet/models/layers.py:32,35) and the 1x1
+ * projections of AttentionGate (layers.py:152,158) as an NHWC bf16 implicit GEMM (TMA ->
+ * smem -> tcgen05.mma -> TMEM).  The input channel axis may span two tensors (in0: C0
+ * channels, in1: C1 channels): torch.cat([x2, x1], dim=1) of Up / AttentionUp (layers.py:105,
+ * :254) without the copy.  wgt: (Cout, taps, C0+C1) bf16.  Epilogue options: per-channel
+ * scale/shift (eval-mode BatchNorm folded, layers.py:33), ReLU (layers.py:34), accumulate into
+ * the destination, split of the output channels over two tensors (channels >= split go to
+ * out1), and per-CTA rows of per-channel sum / sum-of-squares (stats: (stats_rows,2,Cout)
+ * doubles; *stats_rows_used rows are written) for train-mode BatchNorm.  With the
+ * flipped/transposed weight pack it is the data-gradient pass autograd runs for the same conv.
  */
 int ub2_conv_fwd(const void* in0, int ld_in0, int C0, const void* in1, int ld_in1, int C1,
                  const void* wgt, void* out0, int ld0, void* out1, int ld1, int split, int N, int H,
@@ -52,13 +56,137 @@ int ub2_conv_fwd(const void* in0, int ld_in0, int C0, const void* in1, int ld_in
                  int accumulate, double* stats, int stats_rows, int* stats_rows_used,
                  int bn_override, int grid_override, void* stream);
 
-/* ub2_conv_wgrad: the weight-gradient pass of the same nn.Conv2d (autograd of
- * layers.py:32,35,152,158).  Writes split-K partial tiles (splits, taps*(C0+C1), Cout) fp32;
- * ub2_wgrad_reduce folds them, in a fixed order, into the OIHW fp32 .grad tensor.
- */
+/* Weight-gradient pass of the same nn.Conv2d (autograd of layers.py:32,35,152,158): split-K
+ * partial tiles (splits, taps*(C0+C1), Cout) fp32; *splits_used <= max_splits are written. */
 int ub2_conv_wgrad(const void* in0, int ld_in0, int C0, const void* in1, int ld_in1, int C1,
                    const void* dy, int ld_dy, float* partial, int max_splits, int* splits_used,
                    int N, int H, int W, int Cout, int taps, int splits_override, void* stream);
+
+/* grad (Cout,Cin,k,k fp32, the .grad of the nn.Conv2d weight) += sum over splits. */
+int ub2_wgrad_reduce(const float* partial, int splits, int Cout, int Cin, int taps, float* grad,
+                     void* stream);
+
+/* OIHW fp32 parameter -> bf16 packs: fwd (Cout,taps,Cin) and dgrad (Cin,taps flipped,Cout);
+ * either may be NULL; out_scale (optional, per Cout) folds a BatchNorm scale into the pack. */
+int ub2_pack_conv_weight(const float* w, void* fwd, void* dgrad, int Cout, int Cin, int taps,
+                         const float* out_scale, void* stream);
+
+/* ======================= BatchNorm / ReLU / MaxPool passes ============================== */
+
+/* nn.BatchNorm2d in train mode (layers.py:33,36,153,159,165): per-CTA sums -> batch mean and
+ * biased variance; running_mean/var momentum update with the unbiased variance and
+ * num_batches_tracked += 1 (all optional); outputs scale = gamma*invstd, shift = beta -
+ * mean*scale, mean, invstd. */
+int ub2_bn_finalize(const double* partials, int rows, int C, double count, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, long long* nbt,
+                    float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
+                    void* stream);
+/* nn.BatchNorm2d in eval mode: scale/shift from the running statistics. */
+int ub2_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, int C, float* scale, float* shift,
+                       void* stream);
+/* a = relu(scale*y + shift) (nn.ReLU, layers.py:34,37) and, optionally, its 2x2 max-pooled copy
+ * (nn.MaxPool2d(2) of Down, layers.py:56); a or pooled may be NULL; scale/shift NULL = identity. */
+int ub2_bn_act(const void* y, int ld_y, const float* scale, const float* shift, void* a, int ld_a,
+               void* pooled, int ld_p, int N, int H, int W, int C, int relu, void* stream);
+/* Backward of BatchNorm+ReLU(+MaxPool routing) — what autograd runs for layers.py:33-34,56:
+ *   g = (dA + dP routed to the first maximum of each 2x2 window) * [scale*y + shift > 0]
+ *   reduce  : rows of (sum g, sum g*y);  rows = ub2_bn_bwd_rows(...)
+ *   finalize: dgamma/dbeta (+= into the fp32 .grad) and coef (3,C): dy = c0*g + c1*y + c2
+ *             (frozen != 0: eval-mode statistics, c1 = c2 = 0)
+ *   apply   : dy bf16.  dA or dP may be NULL. */
+int ub2_bn_bwd_rows(int N, int H, int W, int C, int pool);
+int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, const void* y, int ld_y,
+                      const float* scale, const float* shift, double* partials, int rows, int N, int H,
+                      int W, int C, int relu, void* stream);
+int ub2_bn_bwd_finalize(const double* partials, int rows, int C, double count, const float* gamma,
+                        const float* mean, const float* invstd, int frozen, float* dgamma, float* dbeta,
+                        float* coef, void* stream);
+int ub2_bn_bwd_apply(const void* dA, int ld_da, const void* dP, int ld_dp, const void* y, int ld_y,
+                     const float* scale, const float* shift, const float* coef, void* dY, int ld_dy,
+                     int N, int H, int W, int C, int relu, void* stream);
+
+/* ======================= bilinear resampling ============================================ */
+
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=True) + F.pad to the skip size
+ * (layers.py:78, :98-102, :212, :247-251): (hin,win) -> (hu,wu) placed centred in (Ho,Wo). */
+int ub2_upsample_fwd(const void* in, int ld_in, void* out, int ld_out, int N, int hin, int win, int hu,
+                     int wu, int Ho, int Wo, int C, void* stream);
+/* Its transpose in gather form (deterministic; ATen's backward uses atomics). */
+int ub2_upsample_bwd(const void* dout, int ld_dout, void* din, int ld_din, int accumulate, int N,
+                     int hin, int win, int hu, int wu, int Ho, int Wo, int C, void* stream);
+
+/* ======================= attention gate (layers.py:171-192) ============================= */
+/* q = W_g.g at low resolution and xp = W_x.x come from ub2_conv_fwd (taps = 1).           */
+
+int ub2_gate_rows(int N, int H, int W, int C);
+/* Batch statistics of F.interpolate(q, (H,W), bilinear, align_corners=True) for BN_g
+ * (layers.py:183,186) without materialising the up-sampled tensor. */
+int ub2_gate_upstats(const void* q, int ld_q, int N, int hin, int win, int H, int W, int Ci,
+                     double* partials, int rows, void* stream);
+/* psi_raw = w_psi . relu(BN_g(up q) + BN_x(xp)) (layers.py:188, :164) + rows of (sum, sum sq). */
+int ub2_gate_psi(const void* q, int ld_q, const void* xp, int ld_xp, const float* scale_g,
+                 const float* shift_g, const float* scale_x, const float* shift_x, const float* wpsi,
+                 float* psi_raw, double* partials, int rows, int N, int hin, int win, int H, int W,
+                 int Ci, void* stream);
+/* a = sigmoid(BN_psi(psi_raw)); out = x * a (layers.py:165-166, :192). */
+int ub2_gate_apply(const float* psi_raw, const float* scale_psi, const float* shift_psi, const void* x,
+                   int ld_x, void* out, int ld_out, float* a_out, int N, int H, int W, int Cx,
+                   void* stream);
+/* Backward passes (autograd of layers.py:183-192). */
+int ub2_gate_bwd_a(const void* dout, int ld_do, const void* x, int ld_x, const float* a,
+                   const float* psi_raw, void* dx, int ld_dx, float* dpsin, double* partials, int rows,
+                   int N, int H, int W, int Cx, void* stream);
+int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_psi, const void* q,
+                   int ld_q, const void* xp, int ld_xp, const float* scale_g, const float* shift_g,
+                   const float* scale_x, const float* shift_x, const float* mean_g,
+                   const float* invstd_g, const float* mean_x, const float* invstd_x,
+                   const float* wpsi, void* ds, int ld_ds, double* partials, int rows, int N, int hin,
+                   int win, int H, int W, int Ci, void* stream);
+int ub2_gate_bwd_finalize(const double* partials, int rows, int Ci, double count, const float* gamma_x,
+                          const float* invstd_x, const float* gamma_g, const float* invstd_g,
+                          int frozen, float* dgamma_x, float* dbeta_x, float* dgamma_g, float* dbeta_g,
+                          float* dwpsi, float* coef, void* stream);
+int ub2_gate_bwd_xg(const void* ds, int ld_ds, const void* xp, int ld_xp, const void* q, int ld_q,
+                    const float* mean_x, const float* invstd_x, const float* mean_g,
+                    const float* invstd_g, const float* coef, void* dxp, int ld_dxp, void* dgup,
+                    int ld_dg, int N, int hin, int win, int H, int W, int Ci, void* stream);
+
+/* ======================= network ends =================================================== */
+
+/* inc.double_conv.0 (layers.py:32 with in_channels = n_channels <= 4): direct fp32 conv of the
+ * fp32 NCHW input, NHWC bf16 output + BatchNorm statistic rows; and its weight gradient. */
+int ub2_conv_in_rows(int N, int H, int W, int Cout);
+int ub2_conv_in_fwd(const float* x, const float* w, void* y, int ld_y, double* partials, int rows, int N,
+                    int Cin, int H, int W, int Cout, void* stream);
+int ub2_conv_in_wgrad(const float* x, const void* dy, int ld_dy, double* partials, int rows, float* grad,
+                      int N, int Cin, int H, int W, int Cout, void* stream);
+/* OutConv (layers.py:120-123): 1x1 conv with bias to fp32 NCHW logits, and its backward. */
+int ub2_outc_rows(int N, int H, int W, int C);
+int ub2_outc_fwd(const void* a, int ld_a, const float* w, const float* bias, float* logits, int N, int H,
+                 int W, int C, int K, void* stream);
+int ub2_outc_bwd(const float* dlogits, const void* a, int ld_a, const float* w, void* da, int ld_da,
+                 double* partials, int rows, float* dw, float* db, int N, int H, int W, int C, int K,
+                 void* stream);
+
+/* ======================= loss and metrics =============================================== */
+
+/* Per-(image, class) pixel sums of DiceLoss / BalancedCELoss / DiceBCELoss
+ * (unet/utils/loss.py:63-73, :129-148): stats (N,4,C) fp32 = {count, CE sum, intersection,
+ * probability sum}; blocks = ub2_seg_stats_blocks(N, HW). */
+int ub2_seg_stats_blocks(int N, long long HW);
+int ub2_seg_stats(const float* logits, const long long* targets, int N, int C, long long HW,
+                  double* partials, int blocks, float* stats, void* stream);
+/* dL/dlogits from coef (N,3,C) = {dL/dCE, dL/dI, dL/dP}. */
+int ub2_seg_stats_bwd(const float* logits, const long long* targets, const float* coef, int N, int C,
+                      long long HW, float* dlogits, void* stream);
+/* SegmentationMetrics.update (unet/utils/metrics.py:55-84): cm ((C+1),(C+1)) int64 +=
+ * histogram of (target, prediction); row/col C = ignored / out of range.  mode 0: argmax of
+ * fp32 logits (N,C,H,W); 1: int64 class indices; 2: softmax[:,1] > threshold
+ * (scripts/predict.py:155-159), optional uint8 0/255 mask_out. */
+int ub2_confusion(const void* pred, const long long* target, int mode, int N, int C, long long HW,
+                  long long ignore_index, int has_ignore, float threshold, long long* cm,
+                  unsigned char* mask_out, void* stream);
 
 #ifdef __cplusplus
 }

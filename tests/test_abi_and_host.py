@@ -1,0 +1,105 @@
+"""CPU: the C-ABI library loads and exports every symbol include/unetb200.h declares, and the
+host-side mirror of the reference interface behaves (no compute calls: there is no GPU here)."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "unetb200.h")) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\b(ub2_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from unet import _C
+    lib = _C.lib()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/unetb200.h but not exported"
+    assert lib.ub2_version() >= 100
+
+
+def test_header_declares_every_exported_symbol():
+    import subprocess
+    from unet import _C
+    out = subprocess.run(["nm", "-D", "--defined-only", _C.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r"\b(ub2_[a-z0-9_]+)\b", out)))
+    assert exported == _declared_symbols()
+
+
+def test_state_dict_layout_and_default_init_match_reference():
+    from unet.models import AttentionUNet, UNet
+    for attention, kw in ((True, {}), (False, {}), (True, {"deep_supervision": True}), (True, {"bilinear": False})):
+        cls = AttentionUNet if attention else UNet
+        m = cls(1, 2, base_features=16, **kw)
+        shapes = O.state_dict_shapes(base_features=16, attention=attention, **kw)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(shapes.keys())
+        assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    # same seed -> bit-identical default initialisation as the reference constructor
+    fp = torch.load(os.path.join(GOLD, "init_fingerprint.pt"), weights_only=False)
+    torch.manual_seed(42)
+    m = AttentionUNet(1, 2, True, 16)
+    for k, v in m.state_dict().items():
+        s, head = fp[k]
+        assert v.double().sum().item() == s and torch.equal(v.flatten()[:4], head), k
+    assert m.get_num_params() == sum(p.numel() for p in m.parameters())
+    assert AttentionUNet().get_num_params() == 17_612_458
+
+
+def test_modules_survive_deepcopy_and_refuse_cpu_compute():
+    from unet.models import AttentionUNet
+    from unet.utils.loss import DiceBCELoss
+    from unet.utils.metrics import SegmentationMetrics
+    m = AttentionUNet(1, 2, True, 16)
+    c = copy.deepcopy(m)
+    c.load_state_dict(m.state_dict(), strict=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 1, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DiceBCELoss()(torch.zeros(1, 2, 8, 8), torch.zeros(1, 8, 8, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        SegmentationMetrics(2).update(torch.zeros(1, 2, 8, 8), torch.zeros(1, 8, 8, dtype=torch.long))
+
+
+def test_loss_combination_from_statistics():
+    """The O(N*C) part of the losses (host side of the ABI) against the oracle, with the pixel
+    statistics computed by plain torch here."""
+    from unet.utils import loss as L
+    g = torch.load(os.path.join(GOLD, "loss.pt"), weights_only=False)
+    z, t = g["z"], g["t"]
+    p = torch.softmax(z, 1)
+    y = torch.nn.functional.one_hot(t, 2).permute(0, 3, 1, 2).float()
+    cnt = y.sum((2, 3))
+    ce = (-torch.log_softmax(z, 1) * y).sum((2, 3))
+    inter, psum = (p * y).sum((2, 3)), p.sum((2, 3))
+    dice = L._dice_from_stats(cnt, inter, psum, 1.0, 'mean', True)
+    bce = L._balanced_ce_from_stats(cnt, ce, 0.3, 1e-6)
+    assert abs(dice.item() - g["dice"]["value"]) < 1e-5
+    assert abs(bce.item() - g["balanced_ce"]["value"]) < 1e-5
+
+
+def test_metrics_host_side():
+    from unet.utils.metrics import SegmentationMetrics
+    for g in torch.load(os.path.join(GOLD, "metrics.pt"), weights_only=False):
+        m = SegmentationMetrics(g["c"], ignore_index=g["ignore"])
+        assert m.compute()["mean_iou"] == 0.0
+        m.confusion_matrix = g["cm"].numpy()
+        res = m.compute()
+        for k, v in g["result"].items():
+            assert res[k] == v
+        assert m.get_confusion_matrix().dtype == np.int64
+        m.reset()
+        assert m.confusion_matrix.sum() == 0

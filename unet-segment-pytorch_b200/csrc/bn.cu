@@ -21,21 +21,20 @@ namespace ub2 {
 static constexpr int kBnThreads = 256;
 
 // ------------------------------------------------------------------------------ finalize
+// blockDim = (32, 32): see rows_sum in vec.cuh
 __global__ void bn_finalize_kernel(const double* __restrict__ partials, int rows, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, long long* nbt,
                                    float momentum, float eps, float* scale, float* shift, float* mean,
                                    float* invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && nbt != nullptr) *nbt += 1;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s1 += partials[(static_cast<size_t>(r) * 2 + 0) * C + c];
-    s2 += partials[(static_cast<size_t>(r) * 2 + 1) * C + c];
-  }
-  const double m = s1 / count;
-  double var = s2 / count - m * m;
+  __shared__ double smem[2 * 32 * 33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && nbt != nullptr) *nbt += 1;
+  double s[2];
+  rows_sum<2>(partials, rows, C, c, s, smem);
+  if (threadIdx.y != 0 || c >= C) return;
+  const double m = s[0] / count;
+  double var = s[1] / count - m * m;
   if (var < 0.0) var = 0.0;
   const double inv = 1.0 / sqrt(var + static_cast<double>(eps));
   const float g = gamma ? gamma[c] : 1.f;
@@ -126,98 +125,129 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __rest
 }
 
 // ------------------------------------------------------------------------------ backward
-template <bool APPLY>
-__global__ void __launch_bounds__(kBnThreads)
-bn_bwd_kernel(const __nv_bfloat16* __restrict__ dA, int ld_da, const __nv_bfloat16* __restrict__ dP,
-              int ld_dp, const __nv_bfloat16* __restrict__ y, int ld_y,
-              const float* __restrict__ scale, const float* __restrict__ shift,
-              const float* __restrict__ mean, const float* __restrict__ invstd,
-              const float* __restrict__ coef, __nv_bfloat16* dY, int ld_dy, double* partials,
-              int relu, WinGeom g) {
+// g = (dA + dP routed through the 2x2 max-pool) * [scale*y + shift > 0]
+//   reduce : s1 = sum g, s2 = sum g*y          (raw y: the finalize turns s2 into sum g*xhat)
+//   apply  : dy = A*g + B*y + C                (coef rows A, B, C from the finalize)
+struct BwdArgs {
+  const __nv_bfloat16* dA; int ld_da;
+  const __nv_bfloat16* dP; int ld_dp;
+  const __nv_bfloat16* y; int ld_y;
+  const float* scale; const float* shift; const float* coef;
+  __nv_bfloat16* dY; int ld_dy;
+  double* partials;
+  int relu;
+};
+
+template <bool POOL, bool APPLY>
+__global__ void __launch_bounds__(kBnThreads, 2)
+bn_bwd_kernel(BwdArgs a, WinGeom g) {
   extern __shared__ float s_red[];
   const int lanes = blockDim.x / g.cgs;
   const int lane = threadIdx.x / g.cgs;
   const int cg = threadIdx.x % g.cgs;
   const bool active = lane < lanes;
-  F8 sc, sh, mu, is, c1, c2, c3;
+  F8 sc, sh, cA, cB, cC, s1, s2;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = cg * 8 + i;
-    sc.v[i] = scale[c]; sh.v[i] = shift[c]; mu.v[i] = mean[c]; is.v[i] = invstd[c];
-    if (APPLY) {
-      c1.v[i] = coef[c]; c2.v[i] = coef[g.C + c]; c3.v[i] = coef[2 * g.C + c];
-    }
+    sc.v[i] = a.scale[c]; sh.v[i] = a.shift[c];
+    if (APPLY) { cA.v[i] = a.coef[c]; cB.v[i] = a.coef[g.C + c]; cC.v[i] = a.coef[2 * g.C + c]; }
+    s1.v[i] = s2.v[i] = 0.f;
   }
-  F8 s1, s2;
+  auto one_pixel = [&](size_t pix, const F8& yv, F8 gv) {
+    F8 out;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s1.v[i] = s2.v[i] = 0.f;
-  const int Hp = g.H / 2, Wp = g.W / 2;
+    for (int i = 0; i < 8; ++i) {
+      float gs = gv.v[i];
+      if (a.relu && !(fmaf(yv.v[i], sc.v[i], sh.v[i]) > 0.f)) gs = 0.f;
+      if (APPLY) {
+        out.v[i] = fmaf(cA.v[i], gs, fmaf(cB.v[i], yv.v[i], cC.v[i]));
+      } else {
+        s1.v[i] += gs;
+        s2.v[i] = fmaf(gs, yv.v[i], s2.v[i]);
+      }
+    }
+    if (APPLY) store8(a.dY + pix * a.ld_dy + cg * 8, out);
+  };
   if (active) {
-    for (long long wi = static_cast<long long>(blockIdx.x) * lanes + lane; wi < g.windows;
-         wi += static_cast<long long>(gridDim.x) * lanes) {
-      const int wc = static_cast<int>(wi % g.Wc);
-      const int hc = static_cast<int>((wi / g.Wc) % g.Hc);
-      const int n = static_cast<int>(wi / (static_cast<long long>(g.Wc) * g.Hc));
-      F8 yv[4], zv[4];
-      bool inb[4];
+    if (!POOL) {
+      const long long pixels = static_cast<long long>(g.N) * g.H * g.W;
+      const long long stride = static_cast<long long>(gridDim.x) * lanes;
+      long long pix = static_cast<long long>(blockIdx.x) * lanes + lane;
+      // 4 pixels per trip: 8 independent 128-bit loads in flight per thread
+      for (; pix + 3 * stride < pixels; pix += 4 * stride) {
+        F8 yv[4], gv[4];
 #pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const int h = hc * 2 + (d >> 1), w = wc * 2 + (d & 1);
-        inb[d] = (h < g.H && w < g.W);
-        if (inb[d]) {
+        for (int u = 0; u < 4; ++u) {
+          const size_t p = static_cast<size_t>(pix + u * stride);
+          yv[u] = load8_stream(a.y + p * a.ld_y + cg * 8);
+          gv[u] = load8_stream(a.dA + p * a.ld_da + cg * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) one_pixel(static_cast<size_t>(pix + u * stride), yv[u], gv[u]);
+      }
+      for (; pix < pixels; pix += stride) {
+        const size_t p = static_cast<size_t>(pix);
+        one_pixel(p, load8_stream(a.y + p * a.ld_y + cg * 8), load8_stream(a.dA + p * a.ld_da + cg * 8));
+      }
+    } else {
+      const int Hp = g.H / 2, Wp = g.W / 2;
+      for (long long wi = static_cast<long long>(blockIdx.x) * lanes + lane; wi < g.windows;
+           wi += static_cast<long long>(gridDim.x) * lanes) {
+        const int wc = static_cast<int>(wi % g.Wc);
+        const int hc = static_cast<int>((wi / g.Wc) % g.Hc);
+        const int n = static_cast<int>(wi / (static_cast<long long>(g.Wc) * g.Hc));
+        F8 yv[4];
+        bool inb[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          const int h = hc * 2 + (d >> 1), w = wc * 2 + (d & 1);
+          inb[d] = (h < g.H && w < g.W);
+          if (inb[d]) {
+            const size_t pix = (static_cast<size_t>(n) * g.H + h) * g.W + w;
+            yv[d] = load8_stream(a.y + pix * a.ld_y + cg * 8);
+          }
+        }
+        // gradient through the 2x2 max-pool goes to the first maximum of the stored activation
+        const bool pooled_win = hc < Hp && wc < Wp;
+        unsigned amax = 0;  // 2 bits per channel
+        F8 gp;
+        if (pooled_win) {
+          const size_t pp = (static_cast<size_t>(n) * Hp + hc) * Wp + wc;
+          gp = load8_stream(a.dP + pp * a.ld_dp + cg * 8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float best = -INFINITY;
+            unsigned bi = 0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+              float av = fmaf(yv[d].v[i], sc.v[i], sh.v[i]);
+              if (a.relu) av = fmaxf(av, 0.f);
+              av = __bfloat162float(__float2bfloat16_rn(av));
+              if (av > best) { best = av; bi = d; }
+            }
+            amax |= bi << (2 * i);
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          if (!inb[d]) continue;
+          const int h = hc * 2 + (d >> 1), w = wc * 2 + (d & 1);
           const size_t pix = (static_cast<size_t>(n) * g.H + h) * g.W + w;
-          yv[d] = load8_stream(y + pix * ld_y + cg * 8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) zv[d].v[i] = fmaf(yv[d].v[i], sc.v[i], sh.v[i]);
-        }
-      }
-      // gradient through the 2x2 max-pool goes to the first maximum of the stored activation
-      int amax[8];
-      F8 gp;
-      const bool pooled_win = (dP != nullptr) && hc < Hp && wc < Wp;
-      if (pooled_win) {
-        const size_t pp = (static_cast<size_t>(n) * Hp + hc) * Wp + wc;
-        gp = load8_stream(dP + pp * ld_dp + cg * 8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float best = -INFINITY;
-          int bi = 0;
-#pragma unroll
-          for (int d = 0; d < 4; ++d) {
-            float av = relu ? fmaxf(zv[d].v[i], 0.f) : zv[d].v[i];
-            av = __bfloat162float(__float2bfloat16_rn(av));
-            if (av > best) { best = av; bi = d; }
-          }
-          amax[i] = bi;
-        }
-      }
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        if (!inb[d]) continue;
-        const int h = hc * 2 + (d >> 1), w = wc * 2 + (d & 1);
-        const size_t pix = (static_cast<size_t>(n) * g.H + h) * g.W + w;
-        F8 dz;
-        if (dA != nullptr) {
-          dz = load8_stream(dA + pix * ld_da + cg * 8);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dz.v[i] = 0.f;
-        }
-        F8 out;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float gsum = dz.v[i];
-          if (pooled_win && amax[i] == d) gsum += gp.v[i];
-          if (relu && !(zv[d].v[i] > 0.f)) gsum = 0.f;
-          const float xh = (yv[d].v[i] - mu.v[i]) * is.v[i];
-          if (APPLY) {
-            out.v[i] = c1.v[i] * (gsum - c2.v[i] - xh * c3.v[i]);
+          F8 gv;
+          if (a.dA != nullptr) {
+            gv = load8_stream(a.dA + pix * a.ld_da + cg * 8);
           } else {
-            s1.v[i] += gsum;
-            s2.v[i] += gsum * xh;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gv.v[i] = 0.f;
           }
+          if (pooled_win) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (((amax >> (2 * i)) & 3u) == static_cast<unsigned>(d)) gv.v[i] += gp.v[i];
+          }
+          one_pixel(pix, yv[d], gv);
         }
-        if (APPLY) store8(dY + pix * ld_dy + cg * 8, out);
       }
     }
   }
@@ -234,29 +264,35 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ dA, int ld_da, const __nv_bfloat
       for (int l = 0; l < lanes; ++l) acc += static_cast<double>(s_red[static_cast<size_t>(l) * g.cgs * 16 + idx]);
       const int cgi = idx / 16, k = idx % 16;
       const int c = cgi * 8 + (k & 7);
-      partials[(static_cast<size_t>(blockIdx.x) * 2 + (k >> 3)) * g.C + c] = acc;
+      a.partials[(static_cast<size_t>(blockIdx.x) * 2 + (k >> 3)) * g.C + c] = acc;
     }
   }
 }
 
-// dgamma/dbeta accumulate into the fp32 .grad tensors; coef = {gamma*invstd, dbeta/M, dgamma/M}
+// s1 = sum g, s2 = sum g*y  ->  dbeta = s1, dgamma = invstd*(s2 - mean*s1) (accumulated into the
+// fp32 .grad tensors) and the apply coefficients: dy = A*g + B*y + C with
+//   A = gamma*invstd, B = -A*invstd*dgamma/M, C = -A*dbeta/M - B*mean     (B = C = 0 when frozen)
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partials, int rows, int C,
                                        double count, const float* __restrict__ gamma,
-                                       const float* __restrict__ invstd, float* dgamma, float* dbeta,
-                                       float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int r = 0; r < rows; ++r) {
-    s1 += partials[(static_cast<size_t>(r) * 2 + 0) * C + c];
-    s2 += partials[(static_cast<size_t>(r) * 2 + 1) * C + c];
-  }
-  if (dbeta) dbeta[c] += static_cast<float>(s1);
-  if (dgamma) dgamma[c] += static_cast<float>(s2);
-  const float g = gamma ? gamma[c] : 1.f;
-  coef[c] = g * invstd[c];
-  coef[C + c] = static_cast<float>(s1 / count);
-  coef[2 * C + c] = static_cast<float>(s2 / count);
+                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                       int frozen, float* dgamma, float* dbeta, float* coef) {
+  __shared__ double smem[2 * 32 * 33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s[2];
+  rows_sum<2>(partials, rows, C, c, s, smem);
+  if (threadIdx.y != 0 || c >= C) return;
+  const double mu = mean[c], is = invstd[c];
+  const double db = s[0];
+  const double dg = is * (s[1] - mu * s[0]);
+  if (dbeta) dbeta[c] += static_cast<float>(db);
+  if (dgamma) dgamma[c] += static_cast<float>(dg);
+  const double g = gamma ? gamma[c] : 1.0;
+  const double A = g * is;
+  const double B = frozen ? 0.0 : -A * is * dg / count;
+  const double Cc = frozen ? 0.0 : -A * db / count - B * mu;
+  coef[c] = static_cast<float>(A);
+  coef[C + c] = static_cast<float>(B);
+  coef[2 * C + c] = static_cast<float>(Cc);
 }
 
 static int bn_block(int cgs) { return cgs * (kBnThreads / cgs); }
@@ -272,7 +308,7 @@ int ub2_bn_finalize(const double* partials, int rows, int C, double count, const
                     float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
                     void* stream) {
   if (C <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
       partials, rows, C, count, gamma, beta, running_mean, running_var, nbt, momentum, eps, scale,
       shift, mean, invstd);
   return static_cast<int>(cudaGetLastError());
@@ -301,51 +337,62 @@ int ub2_bn_act(const void* y, int ld_y, const float* scale, const float* shift, 
   return static_cast<int>(cudaGetLastError());
 }
 
-int ub2_bn_bwd_rows(int N, int H, int W, int C) {
+static long long bwd_items(const WinGeom& g, bool pool) {
+  return pool ? g.windows : static_cast<long long>(g.N) * g.H * g.W;
+}
+
+int ub2_bn_bwd_rows(int N, int H, int W, int C, int pool) {
   if (C % 8 != 0 || C / 8 > kBnThreads) return UB2_ERR_SHAPE;
   WinGeom g = make_geom(N, H, W, C);
   const int lanes = bn_block(g.cgs) / g.cgs;
-  return stream_grid(g.windows, lanes, num_sms(), 4);
+  return stream_grid((bwd_items(g, pool != 0) + 3) / 4, lanes, num_sms(), 2);
 }
 
 int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, const void* y, int ld_y,
-                      const float* scale, const float* shift, const float* mean, const float* invstd,
-                      double* partials, int rows, int N, int H, int W, int C, int relu, void* stream) {
+                      const float* scale, const float* shift, double* partials, int rows, int N, int H,
+                      int W, int C, int relu, void* stream) {
   if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0) return UB2_ERR_SHAPE;
+  if (dA == nullptr && dP == nullptr) return UB2_ERR_SHAPE;
   WinGeom g = make_geom(N, H, W, C);
+  const bool pool = dP != nullptr;
   const int block = bn_block(g.cgs);
   const int lanes = block / g.cgs;
-  const int grid = stream_grid(g.windows, lanes, num_sms(), 4);
+  const int grid = stream_grid((bwd_items(g, pool) + 3) / 4, lanes, num_sms(), 2);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   const size_t smem = static_cast<size_t>(lanes) * g.cgs * 16 * sizeof(float);
-  bn_bwd_kernel<false><<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp,
-      static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, mean, invstd, nullptr, nullptr, 0,
-      partials, relu, g);
+  BwdArgs a{static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp,
+            static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, nullptr, nullptr, 0, partials, relu};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pool) bn_bwd_kernel<true, false><<<grid, block, smem, s>>>(a, g);
+  else bn_bwd_kernel<false, false><<<grid, block, smem, s>>>(a, g);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_bn_bwd_finalize(const double* partials, int rows, int C, double count, const float* gamma,
-                        const float* invstd, float* dgamma, float* dbeta, float* coef, void* stream) {
+                        const float* mean, const float* invstd, int frozen, float* dgamma, float* dbeta,
+                        float* coef, void* stream) {
   if (C <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      partials, rows, C, count, gamma, invstd, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, rows, C, count, gamma, mean, invstd, frozen, dgamma, dbeta, coef);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_bn_bwd_apply(const void* dA, int ld_da, const void* dP, int ld_dp, const void* y, int ld_y,
-                     const float* scale, const float* shift, const float* mean, const float* invstd,
-                     const float* coef, void* dY, int ld_dy, int N, int H, int W, int C, int relu,
-                     void* stream) {
+                     const float* scale, const float* shift, const float* coef, void* dY, int ld_dy,
+                     int N, int H, int W, int C, int relu, void* stream) {
   if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0) return UB2_ERR_SHAPE;
+  if (dA == nullptr && dP == nullptr) return UB2_ERR_SHAPE;
   WinGeom g = make_geom(N, H, W, C);
+  const bool pool = dP != nullptr;
   const int block = bn_block(g.cgs);
   const int lanes = block / g.cgs;
-  const int grid = stream_grid(g.windows, lanes, num_sms(), 8);
-  bn_bwd_kernel<true><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp,
-      static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, mean, invstd, coef,
-      static_cast<__nv_bfloat16*>(dY), ld_dy, nullptr, relu, g);
+  const int grid = stream_grid((bwd_items(g, pool) + 3) / 4, lanes, num_sms(), 4);
+  BwdArgs a{static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp,
+            static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, coef,
+            static_cast<__nv_bfloat16*>(dY), ld_dy, nullptr, relu};
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pool) bn_bwd_kernel<true, true><<<grid, block, 0, s>>>(a, g);
+  else bn_bwd_kernel<false, true><<<grid, block, 0, s>>>(a, g);
   return static_cast<int>(cudaGetLastError());
 }
 

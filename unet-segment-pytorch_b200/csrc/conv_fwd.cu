@@ -22,8 +22,9 @@
 namespace ub2 {
 
 static constexpr int kMaxStages = 8;
-static constexpr int kThreads = 192;
-static constexpr int kATileBytes = 128 * 64 * 2;  // 16 KB slot
+static constexpr int kEpiWarps = 8;                    // 2 per TMEM lane quarter
+static constexpr int kThreads = 64 + 32 * kEpiWarps;   // TMA warp + MMA warp + epilogue
+static constexpr int kATileBytes = 128 * 64 * 2;       // 16 KB slot
 
 struct FwdSmemHeader {
   uint64_t full[kMaxStages];
@@ -50,6 +51,10 @@ __device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// TAPS: 1 or 9 (unrolled in the producer).  ACC: BatchNorm statistics are kept as per-thread
+// running sums over all tiles of the CTA and reduced across lanes once at the end (needs one
+// 32-column chunk per epilogue warp: Cout <= 64); otherwise a register butterfly per tile.
+template <int TAPS, bool ACC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const ConvFwdParams p) {
@@ -58,35 +63,39 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
   const int stage_bytes = p.stage_bytes;
-  FwdSmemHeader* hdr = reinterpret_cast<FwdSmemHeader*>(tiles + p.stages * stage_bytes);
-  float* s_stats = reinterpret_cast<float*>(hdr + 1);  // [4 warps][2][Cout]
+  const int stages = p.stages;
+  FwdSmemHeader* hdr = reinterpret_cast<FwdSmemHeader*>(tiles + stages * stage_bytes);
+  float* s_stats = reinterpret_cast<float*>(hdr + 1);  // [4 quarters][2][Cout]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int C0 = p.C0;
   const int Ctot = p.C0 + p.C1;
-  const int kchunks = Ctot / p.kc;
-  const int ksteps = p.taps * kchunks;
+  const int kc = p.kc;
+  const int kchunks = Ctot / kc;
   const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = tiles_m * p.n_tiles;
-  const int bn_cols = (p.BN + 31) & ~31;  // TMEM columns per accumulator buffer
+  const int n_tiles = p.n_tiles;
+  const int total_tiles = tiles_m * n_tiles;
+  const int BN = p.BN;
+  const int bn_cols = (BN + 31) & ~31;  // TMEM columns per accumulator buffer
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     if (p.C1 > 0) tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < p.stages; ++i) {
+    for (int i = 0; i < stages; ++i) {
       mbar_init(&hdr->full[i], 1);
       mbar_init(&hdr->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&hdr->tmem_full[i], 1);
-      mbar_init(&hdr->tmem_empty[i], 4);
+      mbar_init(&hdr->tmem_empty[i], kEpiWarps);
     }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&hdr->tmem_base, p.tmem_cols);
   if (warp >= 2 && p.stats != nullptr) {
-    for (int i = threadIdx.x - 64; i < 4 * 2 * p.Cout; i += 128) s_stats[i] = 0.f;
+    for (int i = threadIdx.x - 64; i < 4 * 2 * p.Cout; i += 32 * kEpiWarps) s_stats[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -95,97 +104,112 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const uint32_t tx_bytes = 128u * p.kc * 2u + static_cast<uint32_t>(p.BN) * p.kc * 2u;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % p.n_tiles;
-        const int mt = t / p.n_tiles;
-        const int w0 = (mt % p.tiles_w) * p.BW;
-        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.BH;
-        const int i0 = (mt / (p.tiles_w * p.tiles_h)) * p.BI;
-        const int n0 = nt * p.BN;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
-          for (int kcidx = 0; kcidx < kchunks; ++kcidx) {
-            const int c = kcidx * p.kc;
-            mbar_wait(&hdr->empty[stage], phase ^ 1);
+    // Warp-uniform control flow, one elected lane issues: keeps every operand in uniform
+    // registers (a single-thread loop costs ~10x the instructions per k-step).
+    const uint32_t tx_bytes = 128u * kc * 2u + static_cast<uint32_t>(BN) * kc * 2u;
+    const int tw = p.tiles_w, th = p.tiles_h, BW = p.BW, BH = p.BH, BI = p.BI;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % n_tiles;
+      const int mt = t / n_tiles;
+      const int w0 = (mt % tw) * BW;
+      const int h0 = ((mt / tw) % th) * BH;
+      const int i0 = (mt / (tw * th)) * BI;
+      const int n0 = nt * BN;
+#pragma unroll
+      for (int tap = 0; tap < TAPS; ++tap) {
+        const int dr = (TAPS == 9) ? tap / 3 - 1 : 0;
+        const int ds = (TAPS == 9) ? tap % 3 - 1 : 0;
+        int kb = tap * Ctot;
+        for (int c = 0; c < Ctot; c += kc, ++kb) {
+          mbar_wait(&hdr->empty[stage], phase ^ 1);
+          if (elect_one()) {
             uint8_t* sa = tiles + stage * stage_bytes;
-            uint8_t* sb = sa + kATileBytes;
             mbar_expect_tx(&hdr->full[stage], tx_bytes);
-            if (c < p.C0)
+            if (c < C0)
               tma_load_4d(sa, &tmA0, &hdr->full[stage], c, w0 + ds, h0 + dr, i0);
             else
-              tma_load_4d(sa, &tmA1, &hdr->full[stage], c - p.C0, w0 + ds, h0 + dr, i0);
-            tma_load_2d(sb, &tmB, &hdr->full[stage], tap * Ctot + c, n0);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1;
-            }
+              tma_load_4d(sa, &tmA1, &hdr->full[stage], c - C0, w0 + ds, h0 + dr, i0);
+            tma_load_2d(sa + kATileBytes, &tmB, &hdr->full[stage], tap * Ctot + c, n0);
+          }
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
-      const uint32_t sbo = 16u * p.kc;  // 8 rows of kc bf16
-      const uint32_t ltype = (p.kc == 64) ? 2u : (p.kc == 32) ? 4u : 6u;
-      const int kinner = p.kc / 16;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int as = it & 1;
-        mbar_wait(&hdr->tmem_empty[as], ((it >> 1) & 1) ^ 1);
+    const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t ltype = (kc == 64) ? 2u : (kc == 32) ? 4u : 6u;
+    // descriptor = {hi: SBO (8 rows of kc bf16) | version 1 | swizzle, lo: addr>>4 | LBO 1}
+    const uint32_t desc_hi = ((16u * kc) >> 4) | (1u << 14) | (ltype << 29);
+    const uint32_t a_lo0 = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_lo0 = a_lo0 + (kATileBytes >> 4);
+    const uint32_t stage_inc = static_cast<uint32_t>(stage_bytes) >> 4;
+    const int kinner = kc / 16;
+    const int ksteps = TAPS * kchunks;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&hdr->tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * bn_cols;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&hdr->full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * bn_cols;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(&hdr->full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(tiles + stage * stage_bytes);
-          const uint32_t sb = sa + kATileBytes;
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + stage * stage_inc;
+          const uint32_t b_lo = b_lo0 + stage * stage_inc;
           for (int k = 0; k < kinner; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * 32, 16, sbo, ltype);
-            const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, ltype);
+            const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
+            const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
             umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0);
           }
           umma_commit(&hdr->empty[stage]);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (ks == ksteps - 1) umma_commit(&hdr->tmem_full[as]);
         }
-        umma_commit(&hdr->tmem_full[as]);
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int ew = warp - 2;
+    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2; // column group: chunks j with (j & 1) == grp
     const int row = q * 32 + lane;
     const int w_l = row % p.BW;
     const int h_l = (row / p.BW) % p.BH;
     const int i_l = row / (p.BW * p.BH);
     const int nchunks = bn_cols / 32;
-    float* my_stats = s_stats + ew * 2 * p.Cout;
+    const bool want_stats = p.stats != nullptr;
+    float* my_stats = s_stats + q * 2 * p.Cout;
+    float acc_s[ACC ? 32 : 1], acc_q[ACC ? 32 : 1];
+    if (ACC) {
+#pragma unroll
+      for (int i = 0; i < (ACC ? 32 : 1); ++i) acc_s[i] = acc_q[i] = 0.f;
+    }
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int nt = t % p.n_tiles;
-      const int mt = t / p.n_tiles;
+      const int nt = t % n_tiles;
+      const int mt = t / n_tiles;
       const int w = (mt % p.tiles_w) * p.BW + w_l;
       const int h = ((mt / p.tiles_w) % p.tiles_h) * p.BH + h_l;
       const int n = (mt / (p.tiles_w * p.tiles_h)) * p.BI + i_l;
-      const int n0 = nt * p.BN;
+      const int n0 = nt * BN;
       const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
       const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
       const int as = it & 1;
       mbar_wait(&hdr->tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
-      for (int j = 0; j < nchunks; ++j) {
+      for (int j = grp; j < nchunks; j += 2) {
         uint32_t raw[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn_cols + j * 32, raw);
         tmem_ld_wait();
@@ -199,7 +223,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int c = cbase + g * 8;
-          dvalid[g] = valid && (c < p.Cout) && (c < n0 + p.BN);
+          dvalid[g] = valid && (c < p.Cout) && (c < n0 + BN);
           if (c < p.split)
             dst[g] = p.out0 + pix * p.ld0 + c;
           else
@@ -240,29 +264,42 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
           o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
           if (dvalid[g]) *reinterpret_cast<uint4*>(dst[g]) = o;
-          if (p.stats != nullptr) {
-            // statistics of the values as stored (bf16-rounded), zero for masked pixels
-            const float m = dvalid[g] ? 1.f : 0.f;
-            v[g * 8 + 0] = m * bf16_lo(o.x);
-            v[g * 8 + 1] = m * bf16_hi(o.x);
-            v[g * 8 + 2] = m * bf16_lo(o.y);
-            v[g * 8 + 3] = m * bf16_hi(o.y);
-            v[g * 8 + 4] = m * bf16_lo(o.z);
-            v[g * 8 + 5] = m * bf16_hi(o.z);
-            v[g * 8 + 6] = m * bf16_lo(o.w);
-            v[g * 8 + 7] = m * bf16_hi(o.w);
+          if (want_stats) {
+            // statistics of the values as stored (bf16-rounded): BatchNorm then normalises
+            // exactly the tensor it measured; masked pixels / channels count as 0
+            if (dvalid[g]) {
+              v[g * 8 + 0] = bf16_lo(o.x);
+              v[g * 8 + 1] = bf16_hi(o.x);
+              v[g * 8 + 2] = bf16_lo(o.y);
+              v[g * 8 + 3] = bf16_hi(o.y);
+              v[g * 8 + 4] = bf16_lo(o.z);
+              v[g * 8 + 5] = bf16_hi(o.z);
+              v[g * 8 + 6] = bf16_lo(o.w);
+              v[g * 8 + 7] = bf16_hi(o.w);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[g * 8 + i] = 0.f;
+            }
           }
         }
-        if (p.stats != nullptr) {
-          float sq[32];
+        if (want_stats) {
+          if (ACC) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-          const float s1 = butterfly32(v, lane);
-          const float s2 = butterfly32(sq, lane);
-          const int c = cbase + lane;
-          if (c < p.Cout) {
-            my_stats[c] += s1;
-            my_stats[p.Cout + c] += s2;
+            for (int i = 0; i < (ACC ? 32 : 1); ++i) {
+              acc_s[i] += v[i];
+              acc_q[i] = fmaf(v[i], v[i], acc_q[i]);
+            }
+          } else {
+            float sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+            const float s1 = butterfly32(v, lane);
+            const float s2 = butterfly32(sq, lane);
+            const int c = cbase + lane;
+            if (c < p.Cout) {
+              my_stats[c] += s1;
+              my_stats[p.Cout + c] += s2;
+            }
           }
         }
       }
@@ -270,10 +307,26 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&hdr->tmem_empty[as]);
     }
-    if (p.stats != nullptr) {
-      // combine the four epilogue warps, one double pair per channel per CTA
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = threadIdx.x - 64; c < p.Cout; c += 128) {
+    if (want_stats) {
+      if (ACC) {
+        // one cross-lane reduction for the whole CTA (this warp owns chunk `grp`)
+        float a[32], b[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          a[i] = acc_s[ACC ? i : 0];
+          b[i] = acc_q[ACC ? i : 0];
+        }
+        const float s1 = butterfly32(a, lane);
+        const float s2 = butterfly32(b, lane);
+        const int c = grp * 32 + lane;
+        if (grp < nchunks && c < p.Cout) {
+          my_stats[c] = s1;
+          my_stats[p.Cout + c] = s2;
+        }
+      }
+      // combine the four lane quarters, one double pair per channel per CTA
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * kEpiWarps) {
         double s1 = 0.0, s2 = 0.0;
         for (int e = 0; e < 4; ++e) {
           s1 += static_cast<double>(s_stats[e * 2 * p.Cout + c]);
@@ -373,12 +426,25 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
                       stats_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaSuccess;
+    const int lim = 227 * 1024;
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<9, true>, attr, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<9, false>, attr, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<1, true>, attr, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<1, false>, attr, lim);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  conv_fwd_kernel<<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+  // running-sum statistics need one 32-column chunk per epilogue warp and a single N tile
+  const bool acc = a.stats != nullptr && bn_cols <= 64 && p.n_tiles == 1;
+  if (a.taps == 9) {
+    if (acc) conv_fwd_kernel<9, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+    else conv_fwd_kernel<9, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+  } else {
+    if (acc) conv_fwd_kernel<1, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+    else conv_fwd_kernel<1, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.grid_used) *a.grid_used = grid;

@@ -66,85 +66,107 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
 
-  // item -> (split, n tile, m tile); m fastest so CTAs running together share dy tiles in L2
+  // item -> (split, n tile, m tile); m fastest so CTAs running together share dy tiles in L2.
+  // Producer and MMA warps run warp-uniform loops with one elected lane issuing, so operands
+  // stay in uniform registers (single-thread loops cost several hundred cycles per stage).
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx_bytes = kWATileBytes + static_cast<uint32_t>(b_subs) * p.b_sub_bytes;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-        const int mt = it % p.m_tiles;
-        const int nt = (it / p.m_tiles) % p.n_tiles;
-        const int sp = it / (p.m_tiles * p.n_tiles);
-        const int ch_begin = sp * per_split;
-        const int ch_end = min(ch_begin + per_split, total_chunks);
-        for (int ch = ch_begin; ch < ch_end; ++ch) {
-          const int w0 = (ch % p.chunks_w) * p.BW;
-          const int h0 = ((ch / p.chunks_w) % p.chunks_h) * p.BH;
-          const int i0 = (ch / (p.chunks_w * p.chunks_h)) * p.BI;
-          mbar_wait(&hdr->empty[stage], phase ^ 1);
-          uint8_t* sa = tiles + stage * p.stage_bytes;
-          uint8_t* sb = sa + kWATileBytes;
-          mbar_expect_tx(&hdr->full[stage], tx_bytes);
-          for (int j = 0; j < a_subs; ++j) {
-            int m = mt * 128 + j * p.mc;
-            if (m >= Mtot) m = Mtot - p.mc;  // rows past the end are discarded by the epilogue
-            const int tap = m / Ctot;
-            const int c = m % Ctot;
-            const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
-            const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
-            if (c < p.C0)
-              tma_load_4d(sa + j * p.a_sub_bytes, &tmA0, &hdr->full[stage], c, w0 + ds, h0 + dr, i0);
-            else
-              tma_load_4d(sa + j * p.a_sub_bytes, &tmA1, &hdr->full[stage], c - p.C0, w0 + ds,
-                          h0 + dr, i0);
+    const uint32_t tx_bytes = kWATileBytes + static_cast<uint32_t>(b_subs) * p.b_sub_bytes;
+    const int cw_n = p.chunks_w, ch_n = p.chunks_h;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+      const int mt = it % p.m_tiles;
+      const int nt = (it / p.m_tiles) % p.n_tiles;
+      const int sp = it / (p.m_tiles * p.n_tiles);
+      const int ch_begin = sp * per_split;
+      const int ch_end = min(ch_begin + per_split, total_chunks);
+      // per sub-box (channel offset, tap shift, source) of this m tile: lane j owns sub-box j
+      int sub_c = 0, sub_ds = 0, sub_dr = 0;
+      if (lane < a_subs) {
+        int m = mt * 128 + lane * p.mc;
+        if (m >= Mtot) m = Mtot - p.mc;  // rows past the end are discarded by the epilogue
+        const int tap = m / Ctot;
+        sub_c = m % Ctot;
+        sub_dr = (p.taps == 9) ? tap / 3 - 1 : 0;
+        sub_ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+      }
+      int cw = ch_begin % cw_n;
+      int chh = (ch_begin / cw_n) % ch_n;
+      int cn = ch_begin / (cw_n * ch_n);
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int w0 = cw * p.BW, h0 = chh * p.BH, i0 = cn * p.BI;
+        mbar_wait(&hdr->empty[stage], phase ^ 1);
+        uint8_t* sa = tiles + stage * p.stage_bytes;
+        if (lane == 0) mbar_expect_tx(&hdr->full[stage], tx_bytes);
+        __syncwarp();
+        if (lane < a_subs) {
+          if (sub_c < p.C0)
+            tma_load_4d(sa + lane * p.a_sub_bytes, &tmA0, &hdr->full[stage], sub_c, w0 + sub_ds,
+                        h0 + sub_dr, i0);
+          else
+            tma_load_4d(sa + lane * p.a_sub_bytes, &tmA1, &hdr->full[stage], sub_c - p.C0, w0 + sub_ds,
+                        h0 + sub_dr, i0);
+        } else if (lane - a_subs < b_subs) {
+          const int j = lane - a_subs;
+          tma_load_4d(sa + kWATileBytes + j * p.b_sub_bytes, &tmDY, &hdr->full[stage], nt * p.BN + j * 64,
+                      w0, h0, i0);
+        }
+        if (++cw == cw_n) {
+          cw = 0;
+          if (++chh == ch_n) {
+            chh = 0;
+            ++cn;
           }
-          for (int j = 0; j < b_subs; ++j)
-            tma_load_4d(sb + j * p.b_sub_bytes, &tmDY, &hdr->full[stage], nt * p.BN + j * 64, w0, h0,
-                        i0);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);  // both operands MN-major
-      const uint32_t a_pitch = p.mc * 2;                        // bytes per pixel row in an A sub-box
-      const uint32_t a_ltype = (p.mc == 64) ? 2u : (p.mc == 32) ? 4u : 6u;
-      const uint32_t a_sbo = 8 * a_pitch;
-      const uint32_t a_kadv = 16 * a_pitch;
-      int stage = 0;
-      uint32_t phase = 0;
-      int n = 0;
-      for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++n) {
-        const int sp = it / (p.m_tiles * p.n_tiles);
-        const int ch_begin = sp * per_split;
-        const int ch_end = min(ch_begin + per_split, total_chunks);
-        const int as = n & 1;
-        mbar_wait(&hdr->tmem_empty[as], ((n >> 1) & 1) ^ 1);
+    const uint32_t idesc = make_idesc_bf16(128, p.BN, 1, 1);  // both operands MN-major
+    const uint32_t a_pitch = p.mc * 2;                        // bytes per pixel row in an A sub-box
+    const uint32_t a_ltype = (p.mc == 64) ? 2u : (p.mc == 32) ? 4u : 6u;
+    // descriptors: hi = SBO (8 pixel rows) | version | swizzle ; lo = addr>>4 | LBO (sub-box stride)
+    const uint32_t a_hi = ((8 * a_pitch) >> 4) | (1u << 14) | (a_ltype << 29);
+    const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | ((static_cast<uint32_t>(p.a_sub_bytes) >> 4) << 16);
+    const uint32_t b_lo0 = (((smem_u32(tiles) + kWATileBytes) & 0x3FFFFu) >> 4) |
+                           ((static_cast<uint32_t>(p.b_sub_bytes) >> 4) << 16);
+    const uint32_t a_kadv = (16 * a_pitch) >> 4;
+    const uint32_t stage_inc = static_cast<uint32_t>(p.stage_bytes) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int n = 0;
+    for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++n) {
+      const int sp = it / (p.m_tiles * p.n_tiles);
+      const int ch_begin = sp * per_split;
+      const int ch_end = min(ch_begin + per_split, total_chunks);
+      const int as = n & 1;
+      mbar_wait(&hdr->tmem_empty[as], ((n >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * bn_cols;
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        mbar_wait(&hdr->full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * bn_cols;
-        for (int ch = ch_begin; ch < ch_end; ++ch) {
-          mbar_wait(&hdr->full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(tiles + stage * p.stage_bytes);
-          const uint32_t sb = sa + kWATileBytes;
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + stage * stage_inc;
+          const uint32_t b_lo = b_lo0 + stage * stage_inc;
 #pragma unroll
           for (int k = 0; k < kKPix / 16; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * a_kadv, p.a_sub_bytes, a_sbo, a_ltype);
-            const uint64_t db = make_smem_desc(sb + k * 2048, p.b_sub_bytes, 1024, 2u);
+            const uint64_t da = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * a_kadv);
+            const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * (2048u >> 4));
             umma_bf16(d_tmem, da, db, idesc, (ch > ch_begin) || (k > 0));
           }
           umma_commit(&hdr->empty[stage]);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (ch == ch_end - 1) umma_commit(&hdr->tmem_full[as]);
         }
-        umma_commit(&hdr->tmem_full[as]);
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {

@@ -206,12 +206,10 @@ gate_apply_kernel(const float* __restrict__ psi_raw, const float* __restrict__ s
 __global__ void __launch_bounds__(kGateThreads)
 gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_bfloat16* __restrict__ x,
                   int ld_x, const float* __restrict__ a, const float* __restrict__ psi_raw,
-                  const float* __restrict__ mean_psi, const float* __restrict__ invstd_psi,
                   __nv_bfloat16* __restrict__ dx, int ld_dx, float* __restrict__ dpsin,
                   double* partials, GateGeom g) {
   __shared__ float smem[kGateThreads / 32];
-  const float mu = __ldg(mean_psi), is = __ldg(invstd_psi);
-  float st[2] = {0.f, 0.f};
+  float st[2] = {0.f, 0.f};  // sum dn, sum dn*psi_raw (bn_bwd_finalize convention)
   GATE_PIXEL_LOOP(g) {
     GATE_PIX(g)
     const float av = pv ? __ldg(a + pix) : 0.f;
@@ -235,7 +233,7 @@ gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_
       const float dn = dot * av * (1.f - av);
       dpsin[pix] = dn;
       st[0] += dn;
-      st[1] = fmaf(dn, (__ldg(psi_raw + pix) - mu) * is, st[1]);
+      st[1] = fmaf(dn, __ldg(psi_raw + pix), st[1]);
     }
   }
   block_reduce_scalars<2>(st, partials + static_cast<size_t>(blockIdx.x) * 2, smem);
@@ -244,8 +242,7 @@ gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_
 // ds_c = dpsi_raw * w_psi_c * [t_c > 0]; channel sums: ds, ds*xhat_x, ds*xhat_g, dpsi_raw*relu(t)
 __global__ void __launch_bounds__(kGateThreads)
 gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi_raw,
-                  const float* __restrict__ coef_psi, const float* __restrict__ mean_psi,
-                  const float* __restrict__ invstd_psi, const __nv_bfloat16* __restrict__ q, int ld_q,
+                  const float* __restrict__ coef_psi, const __nv_bfloat16* __restrict__ q, int ld_q,
                   const __nv_bfloat16* __restrict__ xp, int ld_xp, const float* __restrict__ sg,
                   const float* __restrict__ hg, const float* __restrict__ sx,
                   const float* __restrict__ hx, const float* __restrict__ mean_g,
@@ -253,8 +250,7 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
                   const float* __restrict__ invstd_x, const float* __restrict__ wpsi,
                   __nv_bfloat16* __restrict__ ds, int ld_ds, double* partials, GateGeom g) {
   __shared__ float smem[kGateThreads * 8];
-  const float c1 = __ldg(coef_psi), c2 = __ldg(coef_psi + 1), c3 = __ldg(coef_psi + 2);
-  const float mu = __ldg(mean_psi), is = __ldg(invstd_psi);
+  const float cA = __ldg(coef_psi), cB = __ldg(coef_psi + 1), cC = __ldg(coef_psi + 2);
   float acc[kMaxG][4][8];
 #pragma unroll
   for (int a = 0; a < kMaxG; ++a)
@@ -265,8 +261,8 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
   GATE_PIXEL_LOOP(g) {
     GATE_PIX(g)
     GATE_DECODE(g)
-    const float ph = pv ? (__ldg(psi_raw + pix) - mu) * is : 0.f;
-    const float dpr = pv ? c1 * (__ldg(dpsin + pix) - c2 - ph * c3) : 0.f;
+    // BN_psi backward: d psi_raw = A*dn + B*psi_raw + C
+    const float dpr = pv ? fmaf(cA, __ldg(dpsin + pix), fmaf(cB, __ldg(psi_raw + pix), cC)) : 0.f;
 #pragma unroll
     for (int gi = 0; gi < kMaxG; ++gi) {
       const int cg = j + gi * g.tpp;
@@ -294,29 +290,31 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
 }
 
 // coef rows: 0..2 = BN_x {gamma*invstd, sum(ds)/M, sum(ds*xhat_x)/M}; 3..5 = BN_g
+// blockDim = (32, 32): see rows_sum in vec.cuh
 __global__ void gate_bwd_finalize_kernel(const double* __restrict__ partials, int rows, int C,
                                          double count, const float* __restrict__ gamma_x,
                                          const float* __restrict__ invstd_x,
                                          const float* __restrict__ gamma_g,
-                                         const float* __restrict__ invstd_g, float* dgamma_x,
+                                         const float* __restrict__ invstd_g, int frozen, float* dgamma_x,
                                          float* dbeta_x, float* dgamma_g, float* dbeta_g, float* dwpsi,
                                          float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int r = 0; r < rows; ++r)
-    for (int k = 0; k < 4; ++k) s[k] += partials[(static_cast<size_t>(r) * 4 + k) * C + c];
+  __shared__ double smem[4 * 32 * 33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s[4];
+  rows_sum<4>(partials, rows, C, c, s, smem);
+  if (threadIdx.y != 0 || c >= C) return;
   if (dbeta_x) dbeta_x[c] += static_cast<float>(s[0]);
   if (dgamma_x) dgamma_x[c] += static_cast<float>(s[1]);
   if (dbeta_g) dbeta_g[c] += static_cast<float>(s[0]);
   if (dgamma_g) dgamma_g[c] += static_cast<float>(s[2]);
   if (dwpsi) dwpsi[c] += static_cast<float>(s[3]);
+  const double inv_m = frozen ? 0.0 : 1.0 / count;
   coef[0 * C + c] = gamma_x[c] * invstd_x[c];
-  coef[1 * C + c] = static_cast<float>(s[0] / count);
-  coef[2 * C + c] = static_cast<float>(s[1] / count);
+  coef[1 * C + c] = static_cast<float>(s[0] * inv_m);
+  coef[2 * C + c] = static_cast<float>(s[1] * inv_m);
   coef[3 * C + c] = gamma_g[c] * invstd_g[c];
-  coef[4 * C + c] = static_cast<float>(s[0] / count);
-  coef[5 * C + c] = static_cast<float>(s[2] / count);
+  coef[4 * C + c] = static_cast<float>(s[0] * inv_m);
+  coef[5 * C + c] = static_cast<float>(s[2] * inv_m);
 }
 
 // dxp = BN_x backward of ds; dgup = BN_g backward of ds (full resolution, later up-sample^T)
@@ -405,22 +403,21 @@ int ub2_gate_apply(const float* psi_raw, const float* scale_psi, const float* sh
 }
 
 int ub2_gate_bwd_a(const void* dout, int ld_do, const void* x, int ld_x, const float* a,
-                   const float* psi_raw, const float* mean_psi, const float* invstd_psi, void* dx,
-                   int ld_dx, float* dpsin, double* partials, int rows, int N, int H, int W, int Cx,
-                   void* stream) {
+                   const float* psi_raw, void* dx, int ld_dx, float* dpsin, double* partials, int rows,
+                   int N, int H, int W, int Cx, void* stream) {
   GateGeom g;
   int rc = make_gate_geom(&g, N, H, W, Cx, 1, 1);
   if (rc) return rc;
   const int grid = gate_grid(g, 4);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   gate_bwd_a_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, mean_psi, invstd_psi,
-      static_cast<bf>(dx), ld_dx, dpsin, partials, g);
+      static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, static_cast<bf>(dx), ld_dx,
+      dpsin, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
-int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_psi,
-                   const float* mean_psi, const float* invstd_psi, const void* q, int ld_q,
+int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_psi, const void* q,
+                   int ld_q,
                    const void* xp, int ld_xp, const float* scale_g, const float* shift_g,
                    const float* scale_x, const float* shift_x, const float* mean_g,
                    const float* invstd_g, const float* mean_x, const float* invstd_x,
@@ -432,7 +429,7 @@ int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_p
   const int grid = gate_grid(g, 4);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   gate_bwd_s_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      dpsin, psi_raw, coef_psi, mean_psi, invstd_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp),
+      dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp),
       ld_xp, scale_g, shift_g, scale_x, shift_x, mean_g, invstd_g, mean_x, invstd_x, wpsi,
       static_cast<bf>(ds), ld_ds, partials, g);
   return static_cast<int>(cudaGetLastError());
@@ -440,12 +437,12 @@ int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_p
 
 int ub2_gate_bwd_finalize(const double* partials, int rows, int Ci, double count, const float* gamma_x,
                           const float* invstd_x, const float* gamma_g, const float* invstd_g,
-                          float* dgamma_x, float* dbeta_x, float* dgamma_g, float* dbeta_g,
+                          int frozen, float* dgamma_x, float* dbeta_x, float* dgamma_g, float* dbeta_g,
                           float* dwpsi, float* coef, void* stream) {
   if (Ci <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  gate_bwd_finalize_kernel<<<(Ci + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      partials, rows, Ci, count, gamma_x, invstd_x, gamma_g, invstd_g, dgamma_x, dbeta_x, dgamma_g,
-      dbeta_g, dwpsi, coef);
+  gate_bwd_finalize_kernel<<<(Ci + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, rows, Ci, count, gamma_x, invstd_x, gamma_g, invstd_g, frozen, dgamma_x, dbeta_x,
+      dgamma_g, dbeta_g, dwpsi, coef);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -136,15 +136,17 @@ conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
   }
 }
 
-// grad[co][ci][t] += sum_rows partials[row][ci][t][co]
+// grad[co][ci][t] += sum_rows partials[row][ci][t][co];  blockDim = (32, 32)
 __global__ void conv_in_wgrad_finalize_kernel(const double* __restrict__ partials, int rows, int Cin,
                                               int Cout, float* grad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Cout * Cin * 9) return;
-  const int co = i / (Cin * 9), r = i % (Cin * 9);
-  double a = 0.0;
-  for (int row = 0; row < rows; ++row) a += partials[(static_cast<size_t>(row) * Cin * 9 + r) * Cout + co];
-  grad[i] += static_cast<float>(a);
+  __shared__ double smem[32 * 33];
+  const int total = Cout * Cin * 9;
+  const int i = blockIdx.x * 32 + threadIdx.x;  // index into the [ci][t][co] row layout
+  double s[1];
+  rows_sum<1>(partials, rows, total, i, s, smem);
+  if (threadIdx.y != 0 || i >= total) return;
+  const int co = i % Cout, r = i / Cout;
+  grad[co * Cin * 9 + r] += static_cast<float>(s[0]);
 }
 
 // ------------------------------------------------------------------------------ outc
@@ -280,17 +282,19 @@ outc_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ 
   }
 }
 
+// blockDim = (32, 32)
 __global__ void outc_bwd_finalize_kernel(const double* __restrict__ partials, int rows, int K, int C,
                                          float* dw, float* db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double smem[32 * 33];
   const int total = K * C + K;
-  if (i >= total) return;
-  double a = 0.0;
-  for (int r = 0; r < rows; ++r) a += partials[static_cast<size_t>(r) * total + i];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  double s[1];
+  rows_sum<1>(partials, rows, total, i, s, smem);
+  if (threadIdx.y != 0 || i >= total) return;
   if (i < K * C) {
-    if (dw) dw[i] += static_cast<float>(a);
+    if (dw) dw[i] += static_cast<float>(s[0]);
   } else if (db) {
-    db[i - K * C] += static_cast<float>(a);
+    db[i - K * C] += static_cast<float>(s[0]);
   }
 }
 
@@ -345,7 +349,7 @@ int ub2_conv_in_wgrad(const float* x, const void* dy, int ld_dy, double* partial
   conv_in_wgrad_kernel<<<dim3(grid, Cin), block, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dy),
                                                            ld_dy, partials, N, Cin, H, W, Cout);
   const int total = Cout * Cin * 9;
-  conv_in_wgrad_finalize_kernel<<<(total + 127) / 128, 128, 0, s>>>(partials, grid, Cin, Cout, grad);
+  conv_in_wgrad_finalize_kernel<<<(total + 31) / 32, dim3(32, 32), 0, s>>>(partials, grid, Cin, Cout, grad);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -381,7 +385,7 @@ int ub2_outc_bwd(const float* dlogits, const void* a, int ld_a, const float* w, 
       dlogits, static_cast<const __nv_bfloat16*>(a), ld_a, w, static_cast<__nv_bfloat16*>(da), ld_da,
       partials, g);
   const int total = K * C + K;
-  outc_bwd_finalize_kernel<<<(total + 127) / 128, 128, 0, s>>>(partials, grid, K, C, dw, db);
+  outc_bwd_finalize_kernel<<<(total + 31) / 32, dim3(32, 32), 0, s>>>(partials, grid, K, C, dw, db);
   return static_cast<int>(cudaGetLastError());
 }
 

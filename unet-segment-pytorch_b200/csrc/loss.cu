@@ -85,16 +85,17 @@ seg_stats_kernel(const float* __restrict__ logits, const long long* __restrict__
   }
 }
 
-// stats[n][k][c] (k = cnt, ce, I, P) as fp32
+// stats[n][k][c] (k = cnt, ce, I, P) as fp32;  grid = (ceil(C*4/32), N), blockDim = (32, 32)
 __global__ void seg_stats_finalize_kernel(const double* __restrict__ partials, int blocks, int N, int C,
                                           float* stats) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * C * 4) return;
-  const int n = i / (C * 4), r = i % (C * 4);
+  __shared__ double smem[32 * 33];
+  const int n = blockIdx.y;
+  const int r = blockIdx.x * 32 + threadIdx.x;
+  double s[1];
+  rows_sum<1>(partials + static_cast<size_t>(n) * blocks * C * 4, blocks, C * 4, r, s, smem);
+  if (threadIdx.y != 0 || r >= C * 4) return;
   const int c = r / 4, k = r % 4;
-  double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += partials[(static_cast<size_t>(n) * blocks + b) * C * 4 + r];
-  stats[(static_cast<size_t>(n) * 4 + k) * C + c] = static_cast<float>(s);
+  stats[(static_cast<size_t>(n) * 4 + k) * C + c] = static_cast<float>(s[0]);
 }
 
 // coef[n][3][C] = {dce, dI, dP} (already multiplied by the upstream gradient on the host side)
@@ -139,7 +140,7 @@ template <int C>
 static int launch_stats(const float* logits, const long long* targets, int N, long long HW,
                         double* partials, int blocks, float* stats, cudaStream_t s) {
   seg_stats_kernel<C><<<dim3(blocks, N), kLossThreads, 0, s>>>(logits, targets, HW, partials);
-  seg_stats_finalize_kernel<<<(N * C * 4 + 127) / 128, 128, 0, s>>>(partials, blocks, N, C, stats);
+  seg_stats_finalize_kernel<<<dim3((C * 4 + 31) / 32, N), dim3(32, 32), 0, s>>>(partials, blocks, N, C, stats);
   return static_cast<int>(cudaGetLastError());
 }
 template <int C>

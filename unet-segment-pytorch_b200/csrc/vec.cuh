@@ -69,6 +69,34 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Deterministic cross-block reduction of per-block partial rows laid out [row][NS][C] (doubles).
+// Launch with blockDim = (32, 32): x = channel lane (coalesced), y = row group.  Threads with
+// threadIdx.y == 0 return the totals for channel `c`.
+template <int NS>
+__device__ __forceinline__ void rows_sum(const double* __restrict__ partials, int rows, int C, int c,
+                                         double (&out)[NS], double* smem /* [NS][32][33] */) {
+  double acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+  if (c < C) {
+    for (int r = threadIdx.y; r < rows; r += 32) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) acc[k] += partials[(static_cast<size_t>(r) * NS + k) * C + c];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NS; ++k) smem[(k * 32 + threadIdx.y) * 33 + threadIdx.x] = acc[k];
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      double s = 0.0;
+      for (int y = 0; y < 32; ++y) s += smem[(k * 32 + y) * 33 + threadIdx.x];
+      out[k] = s;
+    }
+  }
+}
+
 // Grid for a bandwidth-bound grid-stride kernel: a multiple of the SM count.
 inline int stream_grid(long long work_items, int threads, int sms, int blocks_per_sm = 8) {
   long long need = (work_items + threads - 1) / threads;

@@ -157,24 +157,45 @@ def bn_act(y, scale, shift, relu=True, pool=False, write_act=True):
     return a, p
 
 
-def bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, relu=True):
-    """BatchNorm(+ReLU, + max-pool routing) backward: returns (dy bf16, dgamma, dbeta)."""
+def bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, relu=True, frozen=False):
+    """BatchNorm(+ReLU, + max-pool routing) backward: returns (dy bf16, dgamma, dbeta).
+    ``frozen``: statistics were the running buffers (eval-mode backward), no mean terms."""
     n, h, w, c, ld_y = _nhwc(y)
     ld_da = _nhwc(dA)[4] if dA is not None else 0
     ld_dp = _nhwc(dP)[4] if dP is not None else 0
-    rows = _rows("ub2_bn_bwd_rows", n, h, w, c)
+    rows = _rows("ub2_bn_bwd_rows", n, h, w, c, int(dP is not None))
     dev = y.device
     partials = torch.empty((rows, 2, c), device=dev, dtype=F64)
     _C.call("ub2_bn_bwd_reduce", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(y), ld_y, ptr(scale), ptr(shift),
-            ptr(mean), ptr(invstd), ptr(partials), rows, n, h, w, c, int(relu), stream())
-    grads = torch.zeros((2, c), device=dev, dtype=F32)
-    coef = torch.empty((3, c), device=dev, dtype=F32)
-    _C.call("ub2_bn_bwd_finalize", ptr(partials), rows, c, c_double(float(n * h * w)), ptr(gamma),
-            ptr(invstd), ptr(grads[0]), ptr(grads[1]), ptr(coef), stream())
+            ptr(partials), rows, n, h, w, c, int(relu), stream())
+    dgamma, dbeta, coef = bn_bwd_finalize(partials, n * h * w, gamma, mean, invstd, frozen)
     dy = empty_nhwc(n, h, w, c, dev)
     _C.call("ub2_bn_bwd_apply", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(y), ld_y, ptr(scale), ptr(shift),
-            ptr(mean), ptr(invstd), ptr(coef), ptr(dy), c, n, h, w, c, int(relu), stream())
-    return dy, grads[0], grads[1]
+            ptr(coef), ptr(dy), c, n, h, w, c, int(relu), stream())
+    return dy, dgamma, dbeta
+
+
+def bn_bwd_finalize(partials, count, gamma, mean, invstd, frozen=False):
+    """(sum g, sum g*y) rows -> (dgamma, dbeta, coef[3,C]) with dy = coef0*g + coef1*y + coef2."""
+    rows, _, c = partials.shape
+    grads = torch.zeros((2, c), device=partials.device, dtype=F32)
+    coef = torch.empty((3, c), device=partials.device, dtype=F32)
+    _C.call("ub2_bn_bwd_finalize", ptr(partials), rows, c, c_double(float(count)), ptr(gamma), ptr(mean),
+            ptr(invstd), int(frozen), ptr(grads[0]), ptr(grads[1]), ptr(coef), stream())
+    return grads[0], grads[1], coef
+
+
+def maxpool_bwd(dP, a):
+    """Route the pooled gradient to the first maximum of each 2x2 window of `a` (no BN, no ReLU)."""
+    n, h, w, c, ld = _nhwc(a)
+    dev = a.device
+    ident = torch.zeros((5, c), device=dev, dtype=F32)
+    ident[0].fill_(1.0)   # scale = 1
+    ident[2].fill_(1.0)   # coef A = 1 (B = C = 0, shift = 0)
+    dy = empty_nhwc(n, h, w, c, dev)
+    _C.call("ub2_bn_bwd_apply", ptr(None), 0, ptr(dP), _nhwc(dP)[4], ptr(a), ld, ptr(ident[0]),
+            ptr(ident[1]), ptr(ident[2]), ptr(dy), c, n, h, w, c, 0, stream())
+    return dy
 
 
 # --------------------------------------------------------------------------- resampling
@@ -227,48 +248,37 @@ def gate_apply(psi, spsi, hpsi, x, save_a=True):
     return out, a
 
 
-def gate_bwd_a(dout, x, a, psi, mean_psi, invstd_psi):
+def gate_bwd_a(dout, x, a, psi):
     n, h, w, cx, ld_x = _nhwc(x)
     ld_do = _nhwc(dout)[4]
     dx = empty_nhwc(n, h, w, cx, x.device)
     dpsin = torch.empty((n, h, w), device=x.device, dtype=F32)
     rows = gate_rows(n, h, w, cx)
     partials = torch.empty((rows, 2, 1), device=x.device, dtype=F64)
-    _C.call("ub2_gate_bwd_a", ptr(dout), ld_do, ptr(x), ld_x, ptr(a), ptr(psi), ptr(mean_psi),
-            ptr(invstd_psi), ptr(dx), cx, ptr(dpsin), ptr(partials), rows, n, h, w, cx, stream())
+    _C.call("ub2_gate_bwd_a", ptr(dout), ld_do, ptr(x), ld_x, ptr(a), ptr(psi), ptr(dx), cx, ptr(dpsin),
+            ptr(partials), rows, n, h, w, cx, stream())
     return dx, dpsin, partials
 
 
-def bn_bwd_finalize(partials, count, gamma, invstd):
-    rows, _, c = partials.shape
-    grads = torch.zeros((2, c), device=partials.device, dtype=F32)
-    coef = torch.empty((3, c), device=partials.device, dtype=F32)
-    _C.call("ub2_bn_bwd_finalize", ptr(partials), rows, c, c_double(float(count)), ptr(gamma),
-            ptr(invstd), ptr(grads[0]), ptr(grads[1]), ptr(coef), stream())
-    return grads[0], grads[1], coef
-
-
-def gate_bwd_s(dpsin, psi, coef_psi, mean_psi, invstd_psi, q, xp, sg, hg, sx, hx, mean_g, invstd_g,
-               mean_x, invstd_x, wpsi):
+def gate_bwd_s(dpsin, psi, coef_psi, q, xp, sg, hg, sx, hx, mean_g, invstd_g, mean_x, invstd_x, wpsi):
     n, hin, win, ci, ld_q = _nhwc(q)
     _, h, w, _, ld_xp = _nhwc(xp)
     ds = empty_nhwc(n, h, w, ci, q.device)
     rows = gate_rows(n, h, w, ci)
     partials = torch.empty((rows, 4, ci), device=q.device, dtype=F64)
-    _C.call("ub2_gate_bwd_s", ptr(dpsin), ptr(psi), ptr(coef_psi), ptr(mean_psi), ptr(invstd_psi),
-            ptr(q), ld_q, ptr(xp), ld_xp, ptr(sg), ptr(hg), ptr(sx), ptr(hx), ptr(mean_g),
-            ptr(invstd_g), ptr(mean_x), ptr(invstd_x), ptr(wpsi), ptr(ds), ci, ptr(partials), rows, n,
-            hin, win, h, w, ci, stream())
+    _C.call("ub2_gate_bwd_s", ptr(dpsin), ptr(psi), ptr(coef_psi), ptr(q), ld_q, ptr(xp), ld_xp, ptr(sg),
+            ptr(hg), ptr(sx), ptr(hx), ptr(mean_g), ptr(invstd_g), ptr(mean_x), ptr(invstd_x), ptr(wpsi),
+            ptr(ds), ci, ptr(partials), rows, n, hin, win, h, w, ci, stream())
     return ds, partials
 
 
-def gate_bwd_finalize(partials, count, gamma_x, invstd_x, gamma_g, invstd_g):
+def gate_bwd_finalize(partials, count, gamma_x, invstd_x, gamma_g, invstd_g, frozen=False):
     rows, _, ci = partials.shape
     grads = torch.zeros((5, ci), device=partials.device, dtype=F32)
     coef = torch.empty((6, ci), device=partials.device, dtype=F32)
     _C.call("ub2_gate_bwd_finalize", ptr(partials), rows, ci, c_double(float(count)), ptr(gamma_x),
-            ptr(invstd_x), ptr(gamma_g), ptr(invstd_g), ptr(grads[0]), ptr(grads[1]), ptr(grads[2]),
-            ptr(grads[3]), ptr(grads[4]), ptr(coef), stream())
+            ptr(invstd_x), ptr(gamma_g), ptr(invstd_g), int(frozen), ptr(grads[0]), ptr(grads[1]),
+            ptr(grads[2]), ptr(grads[3]), ptr(grads[4]), ptr(coef), stream())
     # dgamma_x, dbeta_x, dgamma_g, dbeta_g, dwpsi
     return grads, coef
 

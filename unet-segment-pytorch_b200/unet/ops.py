@@ -110,23 +110,7 @@ class ConvBnRelu(torch.autograd.Function):
 
 
 def _bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, batch, relu=True):
-    n, h, w, c = y.shape
-    if batch:
-        return K.bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, relu=relu)
-    # frozen statistics (eval-mode backward): dy = dz * gamma * invstd, no mean terms
-    ld = lambda t: K._nhwc(t)[4] if t is not None else 0
-    rows = K._rows("ub2_bn_bwd_rows", n, h, w, c)
-    partials = torch.empty((rows, 2, c), device=y.device, dtype=torch.float64)
-    K._C.call("ub2_bn_bwd_reduce", K.ptr(dA), ld(dA), K.ptr(dP), ld(dP), K.ptr(y), ld(y), K.ptr(scale),
-              K.ptr(shift), K.ptr(mean), K.ptr(invstd), K.ptr(partials), rows, n, h, w, c, int(relu),
-              K.stream())
-    dgamma, dbeta, coef = K.bn_bwd_finalize(partials, n * h * w, gamma, invstd)
-    coef[1:].zero_()
-    dy = K.empty_nhwc(n, h, w, c, y.device)
-    K._C.call("ub2_bn_bwd_apply", K.ptr(dA), ld(dA), K.ptr(dP), ld(dP), K.ptr(y), ld(y), K.ptr(scale),
-              K.ptr(shift), K.ptr(mean), K.ptr(invstd), K.ptr(coef), K.ptr(dy), c, n, h, w, c, int(relu),
-              K.stream())
-    return dy, dgamma, dbeta
+    return K.bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, relu=relu, frozen=not batch)
 
 
 class ConvInBnRelu(torch.autograd.Function):
@@ -223,15 +207,10 @@ class AttentionGateFn(torch.autograd.Function):
         ci = q.shape[3]
         count = n * h * w
         d = to_nhwc(dout)
-        dx, dpsin, part = K.gate_bwd_a(d, xn, a, psi, mp, ip)
-        dgam_p, dbet_p, coef_p = K.bn_bwd_finalize(part, count, gam_p, ip)
-        if not batch:
-            coef_p[1:].zero_()
-        ds, part2 = K.gate_bwd_s(dpsin, psi, coef_p, mp, ip, q, xp, sg, hg, sx, hx, mg, ig, mx, ix, wpsi)
-        grads, coef = K.gate_bwd_finalize(part2, count, gam_x, ix, gam_g, ig)
-        if not batch:
-            coef[1:3].zero_()
-            coef[4:6].zero_()
+        dx, dpsin, part = K.gate_bwd_a(d, xn, a, psi)
+        dgam_p, dbet_p, coef_p = K.bn_bwd_finalize(part, count, gam_p, mp, ip, frozen=not batch)
+        ds, part2 = K.gate_bwd_s(dpsin, psi, coef_p, q, xp, sg, hg, sx, hx, mg, ig, mx, ix, wpsi)
+        grads, coef = K.gate_bwd_finalize(part2, count, gam_x, ix, gam_g, ig, frozen=not batch)
         dxp, dgup = K.gate_bwd_xg(ds, xp, q, mx, ix, mg, ig, coef)
         dq = K.upsample_bwd(dgup, hin, win, h, w)
         gw_x = torch.zeros(sh_x, device=d.device, dtype=torch.float32)
@@ -297,17 +276,7 @@ class MaxPool2x2(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dp):
         (a,) = ctx.saved_tensors
-        n, h, w, c = a.shape
-        dev = a.device
-        one = torch.ones(c, device=dev)
-        zero = torch.zeros(c, device=dev)
-        coef = torch.cat([one, zero, zero]).contiguous()
-        dpn = to_nhwc(dp)
-        dy = K.empty_nhwc(n, h, w, c, dev)
-        K._C.call("ub2_bn_bwd_apply", K.ptr(None), 0, K.ptr(dpn), K._nhwc(dpn)[4], K.ptr(a), K._nhwc(a)[4],
-                  K.ptr(one), K.ptr(zero), K.ptr(zero), K.ptr(one), K.ptr(coef), K.ptr(dy), c, n, h, w, c, 0,
-                  K.stream())
-        return from_nhwc(dy)
+        return from_nhwc(K.maxpool_bwd(to_nhwc(dp), a))
 
 
 class ConvFn(torch.autograd.Function):
