@@ -36,6 +36,8 @@ extern "C" {
 
 int ub2_version(void);
 int ub2_num_sms(void);
+/* Tuning / A-B testing: 0 = automatic kernel choice, 1 = never use the halo-resident 3x3 kernel. */
+int ub2_set_conv_mode(int mode);
 
 /* ======================= convolutions on tcgen05 tensor cores =========================== */
 
@@ -86,25 +88,27 @@ int ub2_bn_eval_coeffs(const float* gamma, const float* beta, const float* runni
                        const float* running_var, float eps, int C, float* scale, float* shift,
                        void* stream);
 /* a = relu(scale*y + shift) (nn.ReLU, layers.py:34,37) and, optionally, its 2x2 max-pooled copy
- * (nn.MaxPool2d(2) of Down, layers.py:56); a or pooled may be NULL; scale/shift NULL = identity. */
+ * (nn.MaxPool2d(2) of Down, layers.py:56) with pidx (N,H/2,W/2,C) uint8 = window position of each
+ * maximum (first maximum wins, as ATen); a, pooled, pidx may be NULL; scale/shift NULL = identity. */
 int ub2_bn_act(const void* y, int ld_y, const float* scale, const float* shift, void* a, int ld_a,
-               void* pooled, int ld_p, int N, int H, int W, int C, int relu, void* stream);
+               void* pooled, int ld_p, unsigned char* pidx, int N, int H, int W, int C, int relu,
+               void* stream);
 /* Backward of BatchNorm+ReLU(+MaxPool routing) — what autograd runs for layers.py:33-34,56:
- *   g = (dA + dP routed to the first maximum of each 2x2 window) * [scale*y + shift > 0]
+ *   g = (dA + dP routed to the window position pidx saved by ub2_bn_act) * [scale*y + shift > 0]
  *   reduce  : rows of (sum g, sum g*y);  rows = ub2_bn_bwd_rows(...)
  *   finalize: dgamma/dbeta (+= into the fp32 .grad) and coef (3,C): dy = c0*g + c1*y + c2
  *             (frozen != 0: eval-mode statistics, c1 = c2 = 0)
  *   apply   : dy bf16.  dA or dP may be NULL. */
 int ub2_bn_bwd_rows(int N, int H, int W, int C, int pool);
-int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, const void* y, int ld_y,
-                      const float* scale, const float* shift, double* partials, int rows, int N, int H,
-                      int W, int C, int relu, void* stream);
+int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, const unsigned char* pidx,
+                      const void* y, int ld_y, const float* scale, const float* shift, double* partials,
+                      int rows, int N, int H, int W, int C, int relu, void* stream);
 int ub2_bn_bwd_finalize(const double* partials, int rows, int C, double count, const float* gamma,
                         const float* mean, const float* invstd, int frozen, float* dgamma, float* dbeta,
                         float* coef, void* stream);
-int ub2_bn_bwd_apply(const void* dA, int ld_da, const void* dP, int ld_dp, const void* y, int ld_y,
-                     const float* scale, const float* shift, const float* coef, void* dY, int ld_dy,
-                     int N, int H, int W, int C, int relu, void* stream);
+int ub2_bn_bwd_apply(const void* dA, int ld_da, const void* dP, int ld_dp, const unsigned char* pidx,
+                     const void* y, int ld_y, const float* scale, const float* shift, const float* coef,
+                     void* dY, int ld_dy, int N, int H, int W, int C, int relu, void* stream);
 
 /* ======================= bilinear resampling ============================================ */
 

@@ -49,6 +49,11 @@ CASES = [
     (1, 8, 8, 16, 16, 48, 9),       # 32B swizzle path, Cout not a multiple of 32
     (1, 16, 256, 64, 0, 64, 9),     # wide rows (BW = 128)
     (2, 32, 32, 512, 512, 512, 9),  # up1.0-like, long K loop
+    # wide rows (W % 128 == 0): halo-resident kernel
+    (2, 5, 128, 64, 64, 64, 9),     # two sources, H not a multiple of the row block
+    (1, 7, 256, 128, 0, 128, 9),    # two channel chunks, N tile 128
+    (1, 4, 128, 64, 0, 256, 9),     # two N tiles
+    (3, 9, 128, 64, 0, 32, 9),
 ]
 
 
@@ -72,10 +77,11 @@ def test_conv_fwd(n, h, w, c0, c1, cout, taps):
     assert torch.allclose(s[1], (o * o).sum(0), rtol=1e-4, atol=1e-2)
 
 
-def test_conv_fwd_epilogue_options():
+@pytest.mark.parametrize("w", [16, 128])
+def test_conv_fwd_epilogue_options(w):
     from unet import kernels as K
 
-    n, h, w, c, cout = 2, 16, 16, 64, 128
+    n, h, c, cout = 2, 16, 64, 128
     x = _mk(n, h, w, c, 5)
     g = torch.Generator().manual_seed(6)
     wt = (torch.randn(cout, c, 3, 3, generator=g) / 24).to(torch.bfloat16)

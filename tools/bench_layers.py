@@ -66,9 +66,10 @@ def main():
     nbytes = y.numel() * 2
     t = timeit(lambda: K.bn_act(y, sc, sh, True, True))
     print(f"bn_act+pool   {t:.3f} ms  {2.25 * nbytes / t / 1e6:.0f} GB/s")
-    t = timeit(lambda: K.bn_backward(dA, None, y, sc, sh, sh, sc, sc))
+    t = timeit(lambda: K.bn_backward(dA, None, None, y, sc, sh, sh, sc, sc))
     print(f"bn_backward   {t:.3f} ms  {5 * nbytes / t / 1e6:.0f} GB/s (reduce+finalize+apply)")
-    t = timeit(lambda: K.bn_backward(dA, dP, y, sc, sh, sh, sc, sc))
+    pidx = K.bn_act(y, sc, sh, True, True, want_idx=True)[2]
+    t = timeit(lambda: K.bn_backward(dA, dP, pidx, y, sc, sh, sh, sc, sc))
     print(f"bn_backward+pool {t:.3f} ms  {5.5 * nbytes / t / 1e6:.0f} GB/s")
     t = timeit(lambda: K.upsample(dP, h, h, h, h))
     print(f"upsample fwd  {t:.3f} ms  {1.25 * nbytes / t / 1e6:.0f} GB/s")

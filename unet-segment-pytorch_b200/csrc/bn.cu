@@ -64,13 +64,17 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
 // ------------------------------------------------------------------------------ window walk
 struct WinGeom {
   int N, H, W, C, cgs, Hc, Wc;
-  long long windows;
+  int windows;
 };
+// Device loops index pixels with 32-bit integers.
+static bool fits32(int N, int H, int W, int C) {
+  return static_cast<double>(N) * H * W * (C > 8 ? C / 8 : 1) < 2.0e9;
+}
 static WinGeom make_geom(int N, int H, int W, int C) {
   WinGeom g;
   g.N = N; g.H = H; g.W = W; g.C = C; g.cgs = C / 8;
   g.Hc = (H + 1) / 2; g.Wc = (W + 1) / 2;
-  g.windows = static_cast<long long>(N) * g.Hc * g.Wc;
+  g.windows = static_cast<int>(N) * g.Hc * g.Wc;
   return g;
 }
 
@@ -78,7 +82,7 @@ static WinGeom make_geom(int N, int H, int W, int C) {
 __global__ void __launch_bounds__(kBnThreads)
 bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __restrict__ scale,
               const float* __restrict__ shift, __nv_bfloat16* a, int ld_a, __nv_bfloat16* pooled,
-              int ld_p, int relu, WinGeom g) {
+              int ld_p, unsigned char* pidx, int relu, WinGeom g) {
   const int lanes = blockDim.x / g.cgs;
   const int lane = threadIdx.x / g.cgs;
   const int cg = threadIdx.x % g.cgs;
@@ -90,12 +94,15 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __rest
     sh.v[i] = shift ? shift[cg * 8 + i] : 0.f;
   }
   const int Hp = g.H / 2, Wp = g.W / 2;
-  for (long long wi = static_cast<long long>(blockIdx.x) * lanes + lane; wi < g.windows;
-       wi += static_cast<long long>(gridDim.x) * lanes) {
+  for (int wi = static_cast<int>(blockIdx.x) * lanes + lane; wi < g.windows;
+       wi += static_cast<int>(gridDim.x) * lanes) {
     const int wc = static_cast<int>(wi % g.Wc);
     const int hc = static_cast<int>((wi / g.Wc) % g.Hc);
-    const int n = static_cast<int>(wi / (static_cast<long long>(g.Wc) * g.Hc));
+    const int n = static_cast<int>(wi / (static_cast<int>(g.Wc) * g.Hc));
     F8 mx;
+    unsigned arg[8];  // window position of the first maximum, per channel
+#pragma unroll
+    for (int i = 0; i < 8; ++i) arg[i] = 0u;
 #pragma unroll
     for (int i = 0; i < 8; ++i) mx.v[i] = -INFINITY;
 #pragma unroll
@@ -114,12 +121,23 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __rest
         if (a != nullptr) *reinterpret_cast<uint4*>(a + pix * ld_a + cg * 8) = packed;
         const F8 r = unpack8(packed);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx.v[i] = fmaxf(mx.v[i], r.v[i]);
+        for (int i = 0; i < 8; ++i) {
+          if (r.v[i] > mx.v[i]) {  // strict: the first maximum wins, as in ATen's max_pool2d
+            mx.v[i] = r.v[i];
+            arg[i] = d;
+          }
+        }
       }
     }
     if (pooled != nullptr && hc < Hp && wc < Wp) {
       const size_t pp = (static_cast<size_t>(n) * Hp + hc) * Wp + wc;
       store8(pooled + pp * ld_p + cg * 8, mx);
+      if (pidx != nullptr) {
+        uint2 packed;  // one byte per channel
+        packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+        packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+        *reinterpret_cast<uint2*>(pidx + pp * g.C + cg * 8) = packed;
+      }
     }
   }
 }
@@ -131,6 +149,7 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __rest
 struct BwdArgs {
   const __nv_bfloat16* dA; int ld_da;
   const __nv_bfloat16* dP; int ld_dp;
+  const unsigned char* pidx;
   const __nv_bfloat16* y; int ld_y;
   const float* scale; const float* shift; const float* coef;
   __nv_bfloat16* dY; int ld_dy;
@@ -171,9 +190,9 @@ bn_bwd_kernel(BwdArgs a, WinGeom g) {
   };
   if (active) {
     if (!POOL) {
-      const long long pixels = static_cast<long long>(g.N) * g.H * g.W;
-      const long long stride = static_cast<long long>(gridDim.x) * lanes;
-      long long pix = static_cast<long long>(blockIdx.x) * lanes + lane;
+      const int pixels = static_cast<int>(g.N) * g.H * g.W;
+      const int stride = static_cast<int>(gridDim.x) * lanes;
+      int pix = static_cast<int>(blockIdx.x) * lanes + lane;
       // 4 pixels per trip: 8 independent 128-bit loads in flight per thread
       for (; pix + 3 * stride < pixels; pix += 4 * stride) {
         F8 yv[4], gv[4];
@@ -192,61 +211,54 @@ bn_bwd_kernel(BwdArgs a, WinGeom g) {
       }
     } else {
       const int Hp = g.H / 2, Wp = g.W / 2;
-      for (long long wi = static_cast<long long>(blockIdx.x) * lanes + lane; wi < g.windows;
-           wi += static_cast<long long>(gridDim.x) * lanes) {
+      for (int wi = static_cast<int>(blockIdx.x) * lanes + lane; wi < g.windows;
+           wi += static_cast<int>(gridDim.x) * lanes) {
         const int wc = static_cast<int>(wi % g.Wc);
         const int hc = static_cast<int>((wi / g.Wc) % g.Hc);
-        const int n = static_cast<int>(wi / (static_cast<long long>(g.Wc) * g.Hc));
-        F8 yv[4];
-        bool inb[4];
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          const int h = hc * 2 + (d >> 1), w = wc * 2 + (d & 1);
-          inb[d] = (h < g.H && w < g.W);
-          if (inb[d]) {
-            const size_t pix = (static_cast<size_t>(n) * g.H + h) * g.W + w;
-            yv[d] = load8_stream(a.y + pix * a.ld_y + cg * 8);
-          }
-        }
-        // gradient through the 2x2 max-pool goes to the first maximum of the stored activation
-        const bool pooled_win = hc < Hp && wc < Wp;
-        unsigned amax = 0;  // 2 bits per channel
-        F8 gp;
-        if (pooled_win) {
+        const int n = static_cast<int>(wi / (static_cast<int>(g.Wc) * g.Hc));
+        const size_t pix0 = (static_cast<size_t>(n) * g.H + hc * 2) * g.W + wc * 2;
+        if (hc < Hp && wc < Wp) {
+          // complete window (the common case): all ten 128-bit loads are issued up front
           const size_t pp = (static_cast<size_t>(n) * Hp + hc) * Wp + wc;
-          gp = load8_stream(a.dP + pp * a.ld_dp + cg * 8);
+          const size_t px[4] = {pix0, pix0 + 1, pix0 + g.W, pix0 + g.W + 1};
+          F8 yv[4], gv[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float best = -INFINITY;
-            unsigned bi = 0;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-              float av = fmaf(yv[d].v[i], sc.v[i], sh.v[i]);
-              if (a.relu) av = fmaxf(av, 0.f);
-              av = __bfloat162float(__float2bfloat16_rn(av));
-              if (av > best) { best = av; bi = d; }
-            }
-            amax |= bi << (2 * i);
-          }
-        }
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          if (!inb[d]) continue;
-          const int h = hc * 2 + (d >> 1), w = wc * 2 + (d & 1);
-          const size_t pix = (static_cast<size_t>(n) * g.H + h) * g.W + w;
-          F8 gv;
+          for (int d = 0; d < 4; ++d) yv[d] = load8_stream(a.y + px[d] * a.ld_y + cg * 8);
+          const F8 gp = load8_stream(a.dP + pp * a.ld_dp + cg * 8);
+          const uint2 amax = __ldg(reinterpret_cast<const uint2*>(a.pidx + pp * g.C + cg * 8));
           if (a.dA != nullptr) {
-            gv = load8_stream(a.dA + pix * a.ld_da + cg * 8);
+#pragma unroll
+            for (int d = 0; d < 4; ++d) gv[d] = load8_stream(a.dA + px[d] * a.ld_da + cg * 8);
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) gv.v[i] = 0.f;
-          }
-          if (pooled_win) {
+            for (int d = 0; d < 4; ++d)
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (((amax >> (2 * i)) & 3u) == static_cast<unsigned>(d)) gv.v[i] += gp.v[i];
+              for (int i = 0; i < 8; ++i) gv[d].v[i] = 0.f;
           }
-          one_pixel(pix, yv[d], gv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const unsigned pos = ((i < 4 ? amax.x : amax.y) >> (8 * (i & 3))) & 3u;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) gv[d].v[i] += (pos == static_cast<unsigned>(d)) ? gp.v[i] : 0.f;
+          }
+#pragma unroll
+          for (int d = 0; d < 4; ++d) one_pixel(px[d], yv[d], gv[d]);
+        } else {
+          // window cut by an odd image edge: its pixels are not pooled (MaxPool2d floors)
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const int h = hc * 2 + (d >> 1), w = wc * 2 + (d & 1);
+            if (h >= g.H || w >= g.W) continue;
+            const size_t pix = (static_cast<size_t>(n) * g.H + h) * g.W + w;
+            F8 gv;
+            if (a.dA != nullptr) {
+              gv = load8_stream(a.dA + pix * a.ld_da + cg * 8);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) gv.v[i] = 0.f;
+            }
+            one_pixel(pix, load8_stream(a.y + pix * a.ld_y + cg * 8), gv);
+          }
         }
       }
     }
@@ -324,8 +336,9 @@ int ub2_bn_eval_coeffs(const float* gamma, const float* beta, const float* runni
 }
 
 int ub2_bn_act(const void* y, int ld_y, const float* scale, const float* shift, void* a, int ld_a,
-               void* pooled, int ld_p, int N, int H, int W, int C, int relu, void* stream) {
-  if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0) return UB2_ERR_SHAPE;
+               void* pooled, int ld_p, unsigned char* pidx, int N, int H, int W, int C, int relu,
+               void* stream) {
+  if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || !fits32(N, H, W, C)) return UB2_ERR_SHAPE;
   if (ld_y % 8 || (a && ld_a % 8) || (pooled && ld_p % 8)) return UB2_ERR_ALIGN;
   WinGeom g = make_geom(N, H, W, C);
   const int block = bn_block(g.cgs);
@@ -333,12 +346,12 @@ int ub2_bn_act(const void* y, int ld_y, const float* scale, const float* shift, 
   const int grid = stream_grid(g.windows, lanes, num_sms(), 8);
   bn_act_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, static_cast<__nv_bfloat16*>(a), ld_a,
-      static_cast<__nv_bfloat16*>(pooled), ld_p, relu, g);
+      static_cast<__nv_bfloat16*>(pooled), ld_p, pidx, relu, g);
   return static_cast<int>(cudaGetLastError());
 }
 
-static long long bwd_items(const WinGeom& g, bool pool) {
-  return pool ? g.windows : static_cast<long long>(g.N) * g.H * g.W;
+static int bwd_items(const WinGeom& g, bool pool) {
+  return pool ? g.windows : static_cast<int>(g.N) * g.H * g.W;
 }
 
 int ub2_bn_bwd_rows(int N, int H, int W, int C, int pool) {
@@ -348,11 +361,11 @@ int ub2_bn_bwd_rows(int N, int H, int W, int C, int pool) {
   return stream_grid((bwd_items(g, pool != 0) + 3) / 4, lanes, num_sms(), 2);
 }
 
-int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, const void* y, int ld_y,
-                      const float* scale, const float* shift, double* partials, int rows, int N, int H,
-                      int W, int C, int relu, void* stream) {
-  if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0) return UB2_ERR_SHAPE;
-  if (dA == nullptr && dP == nullptr) return UB2_ERR_SHAPE;
+int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, const unsigned char* pidx,
+                      const void* y, int ld_y, const float* scale, const float* shift, double* partials,
+                      int rows, int N, int H, int W, int C, int relu, void* stream) {
+  if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || !fits32(N, H, W, C)) return UB2_ERR_SHAPE;
+  if ((dA == nullptr && dP == nullptr) || (dP != nullptr && pidx == nullptr)) return UB2_ERR_SHAPE;
   WinGeom g = make_geom(N, H, W, C);
   const bool pool = dP != nullptr;
   const int block = bn_block(g.cgs);
@@ -360,7 +373,7 @@ int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, cons
   const int grid = stream_grid((bwd_items(g, pool) + 3) / 4, lanes, num_sms(), 2);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   const size_t smem = static_cast<size_t>(lanes) * g.cgs * 16 * sizeof(float);
-  BwdArgs a{static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp,
+  BwdArgs a{static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp, pidx,
             static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, nullptr, nullptr, 0, partials, relu};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (pool) bn_bwd_kernel<true, false><<<grid, block, smem, s>>>(a, g);
@@ -377,17 +390,17 @@ int ub2_bn_bwd_finalize(const double* partials, int rows, int C, double count, c
   return static_cast<int>(cudaGetLastError());
 }
 
-int ub2_bn_bwd_apply(const void* dA, int ld_da, const void* dP, int ld_dp, const void* y, int ld_y,
-                     const float* scale, const float* shift, const float* coef, void* dY, int ld_dy,
-                     int N, int H, int W, int C, int relu, void* stream) {
-  if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0) return UB2_ERR_SHAPE;
-  if (dA == nullptr && dP == nullptr) return UB2_ERR_SHAPE;
+int ub2_bn_bwd_apply(const void* dA, int ld_da, const void* dP, int ld_dp, const unsigned char* pidx,
+                     const void* y, int ld_y, const float* scale, const float* shift, const float* coef,
+                     void* dY, int ld_dy, int N, int H, int W, int C, int relu, void* stream) {
+  if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || !fits32(N, H, W, C)) return UB2_ERR_SHAPE;
+  if ((dA == nullptr && dP == nullptr) || (dP != nullptr && pidx == nullptr)) return UB2_ERR_SHAPE;
   WinGeom g = make_geom(N, H, W, C);
   const bool pool = dP != nullptr;
   const int block = bn_block(g.cgs);
   const int lanes = block / g.cgs;
   const int grid = stream_grid((bwd_items(g, pool) + 3) / 4, lanes, num_sms(), 4);
-  BwdArgs a{static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp,
+  BwdArgs a{static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp, pidx,
             static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, coef,
             static_cast<__nv_bfloat16*>(dY), ld_dy, nullptr, relu};
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -43,9 +43,14 @@ struct ConvFwdParams {
   const float* scale;
   const float* shift;
   double* stats;
+  // halo-resident variant (conv_halo.cu): R output rows x 128 columns per work item
+  int R, segs_w, blocks_h, a_bytes, b_stage_bytes, b_stages;
 };
 
 int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream);
+// Halo-resident 3x3 kernel; returns 1 if the shape is not eligible (caller falls back).
+int conv_halo_launch(const ConvFwdArgs& a, cudaStream_t stream);
+void conv_set_mode(int mode);  // 0 = automatic, 1 = never use the halo kernel (A/B testing)
 
 // ---- wgrad implicit GEMM -----------------------------------------------------------------
 struct ConvWgradArgs {

@@ -17,6 +17,7 @@
 // per-channel sum / sum-of-squares of the rounded outputs (BatchNorm batch
 // statistics, layers.py:33) reduced with a register butterfly.
 #include "conv.h"
+#include "conv_epilogue.cuh"
 #include "ptx.cuh"
 
 namespace ub2 {
@@ -34,22 +35,6 @@ struct FwdSmemHeader {
   uint32_t tmem_base;
   uint32_t pad;
 };
-
-// Reduce 32 columns across the 32 lanes of a warp: on return lane l holds the
-// column-l total in v[0].  31 shuffles instead of 32*5.
-__device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const bool up = (lane & m) != 0;
-#pragma unroll
-    for (int k = 0; k < m; ++k) {
-      float keep = up ? v[k + m] : v[k];
-      float send = up ? v[k] : v[k + m];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-    }
-  }
-  return v[0];
-}
 
 // TAPS: 1 or 9 (unrolled in the producer).  ACC: BatchNorm statistics are kept as per-thread
 // running sums over all tiles of the CTA and reduced across lanes once at the end (needs one
@@ -210,132 +195,15 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       mbar_wait(&hdr->tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
       for (int j = grp; j < nchunks; j += 2) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn_cols + j * 32, raw);
-        tmem_ld_wait();
-        const int cbase = n0 + j * 32;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-        // destination of each 8-channel vector (split output for the dgrad of a virtual concat)
-        __nv_bfloat16* dst[4];
-        bool dvalid[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int c = cbase + g * 8;
-          dvalid[g] = valid && (c < p.Cout) && (c < n0 + BN);
-          if (c < p.split)
-            dst[g] = p.out0 + pix * p.ld0 + c;
-          else
-            dst[g] = p.out1 + pix * p.ld1 + (c - p.split);
-        }
-        if (p.scale != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int c = min(cbase + i, p.Cout - 1);
-            v[i] = fmaf(v[i], __ldg(p.scale + c), __ldg(p.shift + c));
-          }
-        }
-        if (p.accumulate) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (dvalid[g]) {
-              const uint4 o = *reinterpret_cast<const uint4*>(dst[g]);
-              v[g * 8 + 0] += bf16_lo(o.x);
-              v[g * 8 + 1] += bf16_hi(o.x);
-              v[g * 8 + 2] += bf16_lo(o.y);
-              v[g * 8 + 3] += bf16_hi(o.y);
-              v[g * 8 + 4] += bf16_lo(o.z);
-              v[g * 8 + 5] += bf16_hi(o.z);
-              v[g * 8 + 6] += bf16_lo(o.w);
-              v[g * 8 + 7] += bf16_hi(o.w);
-            }
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-          o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-          o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-          o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-          if (dvalid[g]) *reinterpret_cast<uint4*>(dst[g]) = o;
-          if (want_stats) {
-            // statistics of the values as stored (bf16-rounded): BatchNorm then normalises
-            // exactly the tensor it measured; masked pixels / channels count as 0
-            if (dvalid[g]) {
-              v[g * 8 + 0] = bf16_lo(o.x);
-              v[g * 8 + 1] = bf16_hi(o.x);
-              v[g * 8 + 2] = bf16_lo(o.y);
-              v[g * 8 + 3] = bf16_hi(o.y);
-              v[g * 8 + 4] = bf16_lo(o.z);
-              v[g * 8 + 5] = bf16_hi(o.z);
-              v[g * 8 + 6] = bf16_lo(o.w);
-              v[g * 8 + 7] = bf16_hi(o.w);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[g * 8 + i] = 0.f;
-            }
-          }
-        }
-        if (want_stats) {
-          if (ACC) {
-#pragma unroll
-            for (int i = 0; i < (ACC ? 32 : 1); ++i) {
-              acc_s[i] += v[i];
-              acc_q[i] = fmaf(v[i], v[i], acc_q[i]);
-            }
-          } else {
-            float sq[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-            const float s1 = butterfly32(v, lane);
-            const float s2 = butterfly32(sq, lane);
-            const int c = cbase + lane;
-            if (c < p.Cout) {
-              my_stats[c] += s1;
-              my_stats[p.Cout + c] += s2;
-            }
-          }
-        }
+        epi_chunk<ACC>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn_cols + j * 32,
+                       n0 + j * 32, n0 + BN, valid, pix, lane, want_stats, my_stats, acc_s, acc_q);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&hdr->tmem_empty[as]);
     }
-    if (want_stats) {
-      if (ACC) {
-        // one cross-lane reduction for the whole CTA (this warp owns chunk `grp`)
-        float a[32], b[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          a[i] = acc_s[ACC ? i : 0];
-          b[i] = acc_q[ACC ? i : 0];
-        }
-        const float s1 = butterfly32(a, lane);
-        const float s2 = butterfly32(b, lane);
-        const int c = grp * 32 + lane;
-        if (grp < nchunks && c < p.Cout) {
-          my_stats[c] = s1;
-          my_stats[p.Cout + c] = s2;
-        }
-      }
-      // combine the four lane quarters, one double pair per channel per CTA
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * kEpiWarps) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int e = 0; e < 4; ++e) {
-          s1 += static_cast<double>(s_stats[e * 2 * p.Cout + c]);
-          s2 += static_cast<double>(s_stats[e * 2 * p.Cout + p.Cout + c]);
-        }
-        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 0) * p.Cout + c] = s1;
-        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + 1) * p.Cout + c] = s2;
-      }
-    }
+    if (want_stats)
+      epi_finish<ACC, 32 * kEpiWarps>(p, s_stats, my_stats, lane, grp, nchunks, threadIdx.x - 64, acc_s, acc_q);
   }
 
   tc_fence_before();
@@ -356,6 +224,11 @@ static int pow2_floor(int x) {
 }
 
 int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
+  {
+    // wide 3x3 layers: halo block resident in shared memory (conv_halo.cu)
+    const int rc = conv_halo_launch(a, stream);
+    if (rc != 1) return rc;
+  }
   const int Ctot = a.C0 + a.C1;
   if (a.taps != 1 && a.taps != 9) return UB2_ERR_SHAPE;
   if (a.N <= 0 || a.H <= 0 || a.W <= 0 || a.C0 <= 0 || a.C1 < 0) return UB2_ERR_SHAPE;

@@ -261,10 +261,10 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   if (stages > kWMaxStages) stages = kWMaxStages;
   p.stages = stages;
 
-  // split K so that the grid is ~2 waves of work items, each with >= 4 pixel chunks
+  // split K so that the grid is one full wave of work items, each with >= 4 pixel chunks
   const int tiles = p.m_tiles * p.n_tiles;
   const int sms = num_sms();
-  int splits = (2 * sms + tiles - 1) / tiles;
+  int splits = sms / tiles;
   if (splits > total_chunks / 4) splits = total_chunks / 4;
   if (splits < 1) splits = 1;
   if (a.splits_override > 0) splits = a.splits_override;

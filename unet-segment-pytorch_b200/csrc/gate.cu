@@ -26,7 +26,7 @@ static constexpr int kMaxG = 2;  // 8-channel groups per thread (channels <= 512
 
 struct GateGeom {
   int N, H, W, C, cgs, tpp, slots;
-  long long pixels;
+  int pixels;
   LowRes lr;
 };
 
@@ -37,11 +37,12 @@ static int gate_tpp(int cgs) {
 }
 static int make_gate_geom(GateGeom* g, int N, int H, int W, int C, int hin, int win) {
   if (C % 8 != 0 || N <= 0 || H <= 0 || W <= 0) return UB2_ERR_SHAPE;
+  if (static_cast<double>(N) * H * W * (C / 8) >= 2.0e9) return UB2_ERR_SHAPE;  // 32-bit pixel indices
   g->N = N; g->H = H; g->W = W; g->C = C; g->cgs = C / 8;
   g->tpp = gate_tpp(g->cgs);
   if ((g->cgs + g->tpp - 1) / g->tpp > kMaxG) return UB2_ERR_SHAPE;
   g->slots = kGateThreads / g->tpp;
-  g->pixels = static_cast<long long>(N) * H * W;
+  g->pixels = static_cast<int>(N) * H * W;
   g->lr = make_lowres(hin > 0 ? hin : 1, win > 0 ? win : 1, H, W);
   return 0;
 }
@@ -56,11 +57,11 @@ __device__ __forceinline__ float group_sum(float v, int tpp) {
 
 // Reduce per-thread channel accumulators over the pixel slots of a block and write one
 // row of doubles: out_row[ns*C + channel].
-template <int NS>
-__device__ __forceinline__ void block_reduce_channels(float (&acc)[kMaxG][NS][8], const GateGeom& g,
+template <int G, int NS>
+__device__ __forceinline__ void block_reduce_channels(float (&acc)[G][NS][8], const GateGeom& g,
                                                       int slot, int j, double* out_row, float* smem) {
 #pragma unroll
-  for (int gi = 0; gi < kMaxG; ++gi) {
+  for (int gi = 0; gi < G; ++gi) {
 #pragma unroll
     for (int ns = 0; ns < NS; ++ns) {
 #pragma unroll
@@ -101,25 +102,26 @@ __device__ __forceinline__ void block_reduce_scalars(float (&acc)[NS], double* o
 #define GATE_PIXEL_LOOP(g)                                                                  \
   const int slot = threadIdx.x / (g).tpp;                                                   \
   const int j = threadIdx.x % (g).tpp;                                                      \
-  for (long long base = static_cast<long long>(blockIdx.x) * (g).slots; base < (g).pixels;  \
-       base += static_cast<long long>(gridDim.x) * (g).slots)
+  for (int base = static_cast<int>(blockIdx.x) * (g).slots; base < (g).pixels;  \
+       base += static_cast<int>(gridDim.x) * (g).slots)
 
 #define GATE_PIX(g)                     \
-  const long long pix = base + slot;    \
+  const int pix = base + slot;    \
   const bool pv = pix < (g).pixels;
 
 #define GATE_DECODE(g)                                                        \
   const int wo = static_cast<int>(pix % (g).W);                               \
   const int ho = static_cast<int>((pix / (g).W) % (g).H);                     \
-  const int n = static_cast<int>(pix / (static_cast<long long>((g).W) * (g).H));
+  const int n = static_cast<int>(pix / (static_cast<int>((g).W) * (g).H));
 
 // ------------------------------------------------------------------------------ forward
+template <int G>
 __global__ void __launch_bounds__(kGateThreads)
 gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* partials, GateGeom g) {
   __shared__ float smem[kGateThreads * 8];
-  float acc[kMaxG][2][8];
+  float acc[G][2][8];
 #pragma unroll
-  for (int a = 0; a < kMaxG; ++a)
+  for (int a = 0; a < G; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b)
 #pragma unroll
@@ -128,7 +130,7 @@ gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* parti
     GATE_PIX(g)
     GATE_DECODE(g)
 #pragma unroll
-    for (int gi = 0; gi < kMaxG; ++gi) {
+    for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
         const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
@@ -141,9 +143,10 @@ gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* parti
     }
   }
   const int slot2 = threadIdx.x / g.tpp, j2 = threadIdx.x % g.tpp;
-  block_reduce_channels<2>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 2 * g.C, smem);
+  block_reduce_channels<G, 2>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 2 * g.C, smem);
 }
 
+template <int G>
 __global__ void __launch_bounds__(kGateThreads)
 gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat16* __restrict__ xp,
                 int ld_xp, const float* __restrict__ sg, const float* __restrict__ hg,
@@ -157,7 +160,7 @@ gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat
     GATE_DECODE(g)
     float dot = 0.f;
 #pragma unroll
-    for (int gi = 0; gi < kMaxG; ++gi) {
+    for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
         const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
@@ -184,13 +187,13 @@ __global__ void __launch_bounds__(256)
 gate_apply_kernel(const float* __restrict__ psi_raw, const float* __restrict__ spsi,
                   const float* __restrict__ hpsi, const __nv_bfloat16* __restrict__ x, int ld_x,
                   __nv_bfloat16* __restrict__ out, int ld_out, float* __restrict__ a_out,
-                  long long pixels, int cgs) {
+                  int pixels, int cgs) {
   const float s = __ldg(spsi), h = __ldg(hpsi);
-  const long long total = pixels * cgs;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const int total = pixels * cgs;
+  for (int i = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int>(gridDim.x) * blockDim.x) {
     const int cg = static_cast<int>(i % cgs);
-    const long long pix = i / cgs;
+    const int pix = i / cgs;
     const float z = fmaf(__ldg(psi_raw + pix), s, h);
     const float a = 1.f / (1.f + __expf(-z));
     F8 v = load8_stream(x + static_cast<size_t>(pix) * ld_x + cg * 8);
@@ -203,6 +206,7 @@ gate_apply_kernel(const float* __restrict__ psi_raw, const float* __restrict__ s
 
 // ------------------------------------------------------------------------------ backward
 // da = sum_c dOut_c x_c ; d(BN_psi out) = da * a (1-a) ; dx_direct = dOut * a
+template <int G>
 __global__ void __launch_bounds__(kGateThreads)
 gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_bfloat16* __restrict__ x,
                   int ld_x, const float* __restrict__ a, const float* __restrict__ psi_raw,
@@ -215,7 +219,7 @@ gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_
     const float av = pv ? __ldg(a + pix) : 0.f;
     float dot = 0.f;
 #pragma unroll
-    for (int gi = 0; gi < kMaxG; ++gi) {
+    for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
         F8 d = load8_stream(dout + static_cast<size_t>(pix) * ld_do + cg * 8);
@@ -240,6 +244,7 @@ gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_
 }
 
 // ds_c = dpsi_raw * w_psi_c * [t_c > 0]; channel sums: ds, ds*xhat_x, ds*xhat_g, dpsi_raw*relu(t)
+template <int G>
 __global__ void __launch_bounds__(kGateThreads)
 gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi_raw,
                   const float* __restrict__ coef_psi, const __nv_bfloat16* __restrict__ q, int ld_q,
@@ -251,9 +256,9 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
                   __nv_bfloat16* __restrict__ ds, int ld_ds, double* partials, GateGeom g) {
   __shared__ float smem[kGateThreads * 8];
   const float cA = __ldg(coef_psi), cB = __ldg(coef_psi + 1), cC = __ldg(coef_psi + 2);
-  float acc[kMaxG][4][8];
+  float acc[G][4][8];
 #pragma unroll
-  for (int a = 0; a < kMaxG; ++a)
+  for (int a = 0; a < G; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b)
 #pragma unroll
@@ -264,7 +269,7 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
     // BN_psi backward: d psi_raw = A*dn + B*psi_raw + C
     const float dpr = pv ? fmaf(cA, __ldg(dpsin + pix), fmaf(cB, __ldg(psi_raw + pix), cC)) : 0.f;
 #pragma unroll
-    for (int gi = 0; gi < kMaxG; ++gi) {
+    for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
         const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
@@ -286,7 +291,7 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
     }
   }
   const int slot2 = threadIdx.x / g.tpp, j2 = threadIdx.x % g.tpp;
-  block_reduce_channels<4>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 4 * g.C, smem);
+  block_reduce_channels<G, 4>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 4 * g.C, smem);
 }
 
 // coef rows: 0..2 = BN_x {gamma*invstd, sum(ds)/M, sum(ds*xhat_x)/M}; 3..5 = BN_g
@@ -325,11 +330,11 @@ gate_bwd_xg_kernel(const __nv_bfloat16* __restrict__ ds, int ld_ds, const __nv_b
                    const float* __restrict__ mean_g, const float* __restrict__ invstd_g,
                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dxp, int ld_dxp,
                    __nv_bfloat16* __restrict__ dgup, int ld_dg, GateGeom g) {
-  const long long total = g.pixels * g.cgs;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const int total = g.pixels * g.cgs;
+  for (int i = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int>(gridDim.x) * blockDim.x) {
     const int cg = static_cast<int>(i % g.cgs);
-    const long long pix = i / g.cgs;
+    const int pix = i / g.cgs;
     GATE_DECODE(g)
     const F8 d = load8_stream(ds + static_cast<size_t>(pix) * ld_ds + cg * 8);
     const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
@@ -370,8 +375,10 @@ int ub2_gate_upstats(const void* q, int ld_q, int N, int hin, int win, int H, in
   if (rc) return rc;
   const int grid = gate_grid(g, 4);
   if (grid != rows) return UB2_ERR_WORKSPACE;
-  gate_upstats_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<cbf>(q), ld_q, partials, g);
+  if (g.cgs > g.tpp)
+    gate_upstats_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<cbf>(q), ld_q, partials, g);
+  else
+    gate_upstats_kernel<1><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<cbf>(q), ld_q, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -384,17 +391,22 @@ int ub2_gate_psi(const void* q, int ld_q, const void* xp, int ld_xp, const float
   if (rc) return rc;
   const int grid = gate_grid(g, 4);
   if (partials != nullptr && grid != rows) return UB2_ERR_WORKSPACE;
-  gate_psi_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi,
-      psi_raw, partials, g);
+  if (g.cgs > g.tpp)
+    gate_psi_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi,
+        psi_raw, partials, g);
+  else
+    gate_psi_kernel<1><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi,
+        psi_raw, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_gate_apply(const float* psi_raw, const float* scale_psi, const float* shift_psi, const void* x,
                    int ld_x, void* out, int ld_out, float* a_out, int N, int H, int W, int Cx,
                    void* stream) {
-  if (Cx % 8 != 0 || N <= 0) return UB2_ERR_SHAPE;
-  const long long pixels = static_cast<long long>(N) * H * W;
+  if (Cx % 8 != 0 || N <= 0 || static_cast<double>(N) * H * W * (Cx / 8) >= 2.0e9) return UB2_ERR_SHAPE;
+  const int pixels = static_cast<int>(N) * H * W;
   gate_apply_kernel<<<stream_grid(pixels * (Cx / 8), 256, num_sms()), 256, 0,
                       static_cast<cudaStream_t>(stream)>>>(
       psi_raw, scale_psi, shift_psi, static_cast<cbf>(x), ld_x, static_cast<bf>(out), ld_out, a_out,
@@ -410,9 +422,14 @@ int ub2_gate_bwd_a(const void* dout, int ld_do, const void* x, int ld_x, const f
   if (rc) return rc;
   const int grid = gate_grid(g, 4);
   if (grid != rows) return UB2_ERR_WORKSPACE;
-  gate_bwd_a_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, static_cast<bf>(dx), ld_dx,
-      dpsin, partials, g);
+  if (g.cgs > g.tpp)
+    gate_bwd_a_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, static_cast<bf>(dx), ld_dx,
+        dpsin, partials, g);
+  else
+    gate_bwd_a_kernel<1><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, static_cast<bf>(dx), ld_dx,
+        dpsin, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -428,10 +445,14 @@ int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_p
   if (rc) return rc;
   const int grid = gate_grid(g, 4);
   if (grid != rows) return UB2_ERR_WORKSPACE;
-  gate_bwd_s_kernel<<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp),
-      ld_xp, scale_g, shift_g, scale_x, shift_x, mean_g, invstd_g, mean_x, invstd_x, wpsi,
-      static_cast<bf>(ds), ld_ds, partials, g);
+  if (g.cgs > g.tpp)
+    gate_bwd_s_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g,
+        scale_x, shift_x, mean_g, invstd_g, mean_x, invstd_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
+  else
+    gate_bwd_s_kernel<1><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g,
+        scale_x, shift_x, mean_g, invstd_g, mean_x, invstd_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -17,6 +17,9 @@ static constexpr int kMaxClasses = 8;
 static constexpr int kMaxCin = 4;
 
 // ------------------------------------------------------------------------------ conv_in
+// REGW: Cin == 1 and the thread's 8x9 weights live in registers (the shared-memory weight reads
+// otherwise bound the kernel: 18 conflicted LDS.128 per pixel).
+template <bool REGW>
 __global__ void __launch_bounds__(kHeadThreads)
 conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
                    int ld_y, double* partials, int N, int Cin, int H, int W, int Cout) {
@@ -32,40 +35,53 @@ conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __n
   const int lanes = blockDim.x / cgs;
   const int lane = threadIdx.x / cgs, cg = threadIdx.x % cgs;
   const bool active = lane < lanes;
-  const long long pixels = static_cast<long long>(N) * H * W;
+  const int rows = N * H;
+  float wr[REGW ? 9 : 1][8];
+  if (REGW) {
+#pragma unroll
+    for (int t = 0; t < (REGW ? 9 : 1); ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wr[t][k] = s_w[t * Cout + cg * 8 + k];
+  }
   float s1[8], s2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
   if (active) {
-    for (long long pix = static_cast<long long>(blockIdx.x) * lanes + lane; pix < pixels;
-         pix += static_cast<long long>(gridDim.x) * lanes) {
-      const int wq = static_cast<int>(pix % W);
-      const int hq = static_cast<int>((pix / W) % H);
-      const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-      float acc[8];
+    // block walks image rows; its pixel lanes walk the row (no per-pixel integer division)
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int n = row / H, hq = row % H;
+      for (int wq = lane; wq < W; wq += lanes) {
+        const size_t pix = static_cast<size_t>(row) * W + wq;
+        float acc[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-      for (int ci = 0; ci < Cin; ++ci) {
-        const float* xp = x + (static_cast<size_t>(n) * Cin + ci) * H * W;
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float* xp = x + (static_cast<size_t>(n) * Cin + ci) * H * W;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
-          const float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xp + static_cast<size_t>(hh) * W + ww) : 0.f;
-          const float* wr = s_w + (ci * 9 + t) * Cout + cg * 8;
+          for (int t = 0; t < 9; ++t) {
+            const int hh = hq + t / 3 - 1, ww = wq + t % 3 - 1;
+            const float xv = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xp + static_cast<size_t>(hh) * W + ww) : 0.f;
+            if (REGW) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wr[k], acc[k]);
+              for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wr[REGW ? t : 0][k], acc[k]);
+            } else {
+              const float* wrow = s_w + (ci * 9 + t) * Cout + cg * 8;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wrow[k], acc[k]);
+            }
+          }
         }
-      }
-      F8 o;
+        F8 o;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
-      const uint4 packed = pack8(o);
-      *reinterpret_cast<uint4*>(y + static_cast<size_t>(pix) * ld_y + cg * 8) = packed;
-      const F8 r = unpack8(packed);
+        for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
+        const uint4 packed = pack8(o);
+        *reinterpret_cast<uint4*>(y + pix * ld_y + cg * 8) = packed;
+        const F8 r = unpack8(packed);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        s1[k] += r.v[k];
-        s2[k] = fmaf(r.v[k], r.v[k], s2[k]);
+        for (int k = 0; k < 8; ++k) {
+          s1[k] += r.v[k];
+          s2[k] = fmaf(r.v[k], r.v[k], s2[k]);
+        }
       }
     }
   }
@@ -95,18 +111,18 @@ conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
   const int lanes = blockDim.x / cgs;
   const int lane = threadIdx.x / cgs, cg = threadIdx.x % cgs;
   const bool active = lane < lanes;
-  const long long pixels = static_cast<long long>(N) * H * W;
+  const int pixels = static_cast<int>(N) * H * W;
   float acc[9][8];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
   if (active) {
-    for (long long pix = static_cast<long long>(blockIdx.x) * lanes + lane; pix < pixels;
-         pix += static_cast<long long>(gridDim.x) * lanes) {
+    for (int pix = static_cast<int>(blockIdx.x) * lanes + lane; pix < pixels;
+         pix += static_cast<int>(gridDim.x) * lanes) {
       const int wq = static_cast<int>(pix % W);
       const int hq = static_cast<int>((pix / W) % H);
-      const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+      const int n = static_cast<int>(pix / (static_cast<int>(W) * H));
       const F8 d = load8_stream(dy + static_cast<size_t>(pix) * ld_dy + cg * 8);
       const float* xp = x + (static_cast<size_t>(n) * Cin + ci) * H * W;
 #pragma unroll
@@ -152,16 +168,23 @@ __global__ void conv_in_wgrad_finalize_kernel(const double* __restrict__ partial
 // ------------------------------------------------------------------------------ outc
 struct HeadGeom {
   int C, cgs, tpp, slots, K;
-  long long pixels, HW;
+  int pixels, HW;
 };
 
 __global__ void __launch_bounds__(kHeadThreads)
 outc_fwd_kernel(const __nv_bfloat16* __restrict__ a, int ld_a, const float* __restrict__ w,
                 const float* __restrict__ bias, float* __restrict__ logits, HeadGeom g) {
   const int slot = threadIdx.x / g.tpp, j = threadIdx.x % g.tpp;
-  for (long long base = static_cast<long long>(blockIdx.x) * g.slots; base < g.pixels;
-       base += static_cast<long long>(gridDim.x) * g.slots) {
-    const long long pix = base + slot;
+  // one channel group per thread (C <= 256): its weights stay in registers
+  const bool single = g.cgs <= g.tpp;
+  F8 wreg[kMaxClasses];
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    if (single && k < g.K && j < g.cgs) wreg[k] = loadf8(w + static_cast<size_t>(k) * g.C + j * 8);
+  }
+  for (int base = static_cast<int>(blockIdx.x) * g.slots; base < g.pixels;
+       base += static_cast<int>(gridDim.x) * g.slots) {
+    const int pix = base + slot;
     const bool pv = pix < g.pixels;
     float dot[kMaxClasses];
 #pragma unroll
@@ -172,7 +195,7 @@ outc_fwd_kernel(const __nv_bfloat16* __restrict__ a, int ld_a, const float* __re
 #pragma unroll
         for (int k = 0; k < kMaxClasses; ++k) {
           if (k < g.K) {
-            const F8 wv = loadf8(w + static_cast<size_t>(k) * g.C + cg * 8);
+            const F8 wv = single ? wreg[k] : loadf8(w + static_cast<size_t>(k) * g.C + cg * 8);
 #pragma unroll
             for (int i = 0; i < 8; ++i) dot[k] = fmaf(v.v[i], wv.v[i], dot[k]);
           }
@@ -186,7 +209,7 @@ outc_fwd_kernel(const __nv_bfloat16* __restrict__ a, int ld_a, const float* __re
       }
     }
     if (pv && j == 0) {
-      const long long n = pix / g.HW, r = pix % g.HW;
+      const int n = pix / g.HW, r = pix % g.HW;
 #pragma unroll
       for (int k = 0; k < kMaxClasses; ++k)
         if (k < g.K) logits[(n * g.K + k) * g.HW + r] = dot[k] + (bias ? __ldg(bias + k) : 0.f);
@@ -195,28 +218,30 @@ outc_fwd_kernel(const __nv_bfloat16* __restrict__ a, int ld_a, const float* __re
 }
 
 // dA[p][c] = sum_k dl[k][p] W[k][c];  partial rows: [K][C] (dW) then [K] (db), as doubles
+template <int KMAX, int G>
 __global__ void __launch_bounds__(kHeadThreads)
 outc_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int ld_a,
                 const float* __restrict__ w, __nv_bfloat16* __restrict__ da, int ld_da,
                 double* partials, HeadGeom g) {
   extern __shared__ float s_red[];  // [256][8]
   const int slot = threadIdx.x / g.tpp, j = threadIdx.x % g.tpp;
-  // up to 2 channel groups per thread (C <= 512)
-  float accw[2][kMaxClasses][8];
+  // G channel groups per thread (C <= 256*G), KMAX >= n_classes
+  constexpr int kMaxClasses = KMAX;
+  float accw[G][kMaxClasses][8];
   float accb[kMaxClasses];
 #pragma unroll
-  for (int gi = 0; gi < 2; ++gi)
+  for (int gi = 0; gi < G; ++gi)
 #pragma unroll
     for (int k = 0; k < kMaxClasses; ++k)
 #pragma unroll
       for (int i = 0; i < 8; ++i) accw[gi][k][i] = 0.f;
 #pragma unroll
   for (int k = 0; k < kMaxClasses; ++k) accb[k] = 0.f;
-  for (long long base = static_cast<long long>(blockIdx.x) * g.slots; base < g.pixels;
-       base += static_cast<long long>(gridDim.x) * g.slots) {
-    const long long pix = base + slot;
+  for (int base = static_cast<int>(blockIdx.x) * g.slots; base < g.pixels;
+       base += static_cast<int>(gridDim.x) * g.slots) {
+    const int pix = base + slot;
     if (pix >= g.pixels) continue;
-    const long long n = pix / g.HW, r = pix % g.HW;
+    const int n = pix / g.HW, r = pix % g.HW;
     float d[kMaxClasses];
 #pragma unroll
     for (int k = 0; k < kMaxClasses; ++k) {
@@ -224,7 +249,7 @@ outc_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ 
       if (j == 0) accb[k] += d[k];
     }
 #pragma unroll
-    for (int gi = 0; gi < 2; ++gi) {
+    for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (cg < g.cgs) {
         const F8 v = load8_stream(a + static_cast<size_t>(pix) * ld_a + cg * 8);
@@ -248,7 +273,7 @@ outc_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ 
   }
   double* row = partials + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(g.K) * g.C + g.K);
 #pragma unroll
-  for (int gi = 0; gi < 2; ++gi) {
+  for (int gi = 0; gi < G; ++gi) {
 #pragma unroll
     for (int k = 0; k < kMaxClasses; ++k) {
       if (k >= g.K) continue;
@@ -300,12 +325,13 @@ __global__ void outc_bwd_finalize_kernel(const double* __restrict__ partials, in
 
 static int head_geom(HeadGeom* g, int N, int H, int W, int C, int K) {
   if (C % 8 != 0 || K < 1 || K > kMaxClasses || N <= 0) return UB2_ERR_SHAPE;
+  if (static_cast<double>(N) * H * W * K >= 2.0e9) return UB2_ERR_SHAPE;  // 32-bit pixel indices
   g->C = C; g->cgs = C / 8; g->K = K;
   int t = 1;
   while (t < g->cgs && t < 32) t *= 2;
   g->tpp = t;
   g->slots = kHeadThreads / t;
-  g->HW = static_cast<long long>(H) * W;
+  g->HW = static_cast<int>(H) * W;
   g->pixels = g->HW * N;
   return 0;
 }
@@ -319,30 +345,36 @@ extern "C" {
 int ub2_conv_in_rows(int N, int H, int W, int Cout) {
   if (Cout % 8 != 0 || Cout / 8 > kHeadThreads) return UB2_ERR_SHAPE;
   const int lanes = kHeadThreads / (Cout / 8);
-  return stream_grid(static_cast<long long>(N) * H * W, lanes, num_sms(), 4);
+  return stream_grid(static_cast<int>(N) * H * W, lanes, num_sms(), 4);
 }
 
 int ub2_conv_in_fwd(const float* x, const float* w, void* y, int ld_y, double* partials, int rows, int N,
                     int Cin, int H, int W, int Cout, void* stream) {
   if (Cout % 8 != 0 || Cout / 8 > kHeadThreads || Cin < 1 || Cin > kMaxCin) return UB2_ERR_SHAPE;
+  if (static_cast<double>(N) * H * W * Cin >= 2.0e9) return UB2_ERR_SHAPE;  // 32-bit pixel indices
   const int cgs = Cout / 8;
   const int block = cgs * (kHeadThreads / cgs);
   const int lanes = block / cgs;
-  const int grid = stream_grid(static_cast<long long>(N) * H * W, lanes, num_sms(), 4);
+  const int grid = stream_grid(static_cast<int>(N) * H * W, lanes, num_sms(), 4);
   if (partials != nullptr && grid != rows) return UB2_ERR_WORKSPACE;
   const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + static_cast<size_t>(lanes) * cgs * 16) * sizeof(float);
-  conv_in_fwd_kernel<<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
-      x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, Cin, H, W, Cout);
+  if (Cin == 1)
+    conv_in_fwd_kernel<true><<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, Cin, H, W, Cout);
+  else
+    conv_in_fwd_kernel<false><<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, Cin, H, W, Cout);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_conv_in_wgrad(const float* x, const void* dy, int ld_dy, double* partials, int rows, float* grad,
                       int N, int Cin, int H, int W, int Cout, void* stream) {
   if (Cout % 8 != 0 || Cout / 8 > kHeadThreads || Cin < 1 || Cin > kMaxCin) return UB2_ERR_SHAPE;
+  if (static_cast<double>(N) * H * W * Cin >= 2.0e9) return UB2_ERR_SHAPE;  // 32-bit pixel indices
   const int cgs = Cout / 8;
   const int block = cgs * (kHeadThreads / cgs);
   const int lanes = block / cgs;
-  const int grid = stream_grid(static_cast<long long>(N) * H * W, lanes, num_sms(), 4);
+  const int grid = stream_grid(static_cast<int>(N) * H * W, lanes, num_sms(), 4);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   const size_t smem = static_cast<size_t>(lanes) * cgs * 8 * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -381,9 +413,19 @@ int ub2_outc_bwd(const float* dlogits, const void* a, int ld_a, const float* w, 
   const int grid = stream_grid(g.pixels, g.slots, num_sms(), 4);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  outc_bwd_kernel<<<grid, kHeadThreads, kHeadThreads * 8 * sizeof(float), s>>>(
-      dlogits, static_cast<const __nv_bfloat16*>(a), ld_a, w, static_cast<__nv_bfloat16*>(da), ld_da,
-      partials, g);
+  const size_t smem = kHeadThreads * 8 * sizeof(float);
+  const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(a);
+  __nv_bfloat16* dap = static_cast<__nv_bfloat16*>(da);
+  const bool two = g.cgs > g.tpp;
+#define UB2_OUTC_BWD(KM)                                                                              \
+  do {                                                                                                \
+    if (two) outc_bwd_kernel<KM, 2><<<grid, kHeadThreads, smem, s>>>(dlogits, ap, ld_a, w, dap, ld_da, partials, g); \
+    else outc_bwd_kernel<KM, 1><<<grid, kHeadThreads, smem, s>>>(dlogits, ap, ld_a, w, dap, ld_da, partials, g);    \
+  } while (0)
+  if (K <= 2) UB2_OUTC_BWD(2);
+  else if (K <= 4) UB2_OUTC_BWD(4);
+  else UB2_OUTC_BWD(8);
+#undef UB2_OUTC_BWD
   const int total = K * C + K;
   outc_bwd_finalize_kernel<<<(total + 31) / 32, dim3(32, 32), 0, s>>>(partials, grid, K, C, dw, db);
   return static_cast<int>(cudaGetLastError());

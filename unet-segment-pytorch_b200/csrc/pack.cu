@@ -28,21 +28,28 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
-// grad[co][ci][t] += sum_s partial[s][t*Cin + ci][co]
+// grad[co][ci][t] += sum_s partial[s][t*Cin + ci][co];  blockDim = (32, 8): x walks the partial
+// layout (coalesced), y strides over the splits; fixed summation order (deterministic).
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin,
                                     int taps, float* __restrict__ grad) {
+  __shared__ float s_red[8][33];
   const long long total = static_cast<long long>(Cout) * Cin * taps;
-  const long long plane = total;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    // i indexes the partial layout (m = t*Cin + ci, co) so reads are coalesced
+  const long long i = static_cast<long long>(blockIdx.x) * 32 + threadIdx.x;
+  float a = 0.f;
+  if (i < total) {
+    for (int s = threadIdx.y; s < splits; s += 8) a += __ldg(partial + s * total + i);
+  }
+  s_red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < total) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += s_red[y][threadIdx.x];
     const int co = static_cast<int>(i % Cout);
     const long long m = i / Cout;
     const int ci = static_cast<int>(m % Cin);
-    const int t = static_cast<int>(m / Cin);
-    float a = 0.f;
-    for (int s = 0; s < splits; ++s) a += __ldg(partial + s * plane + i);
-    grad[(static_cast<size_t>(co) * Cin + ci) * taps + t] += a;
+    const int tp = static_cast<int>(m / Cin);
+    grad[(static_cast<size_t>(co) * Cin + ci) * taps + tp] += t;
   }
 }
 
@@ -67,8 +74,8 @@ int ub2_wgrad_reduce(const float* partial, int splits, int Cout, int Cin, int ta
                      void* stream) {
   if (Cout <= 0 || Cin <= 0 || splits <= 0) return UB2_ERR_SHAPE;
   const long long total = static_cast<long long>(Cout) * Cin * taps;
-  wgrad_reduce_kernel<<<stream_grid(total, 256, num_sms(), 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      partial, splits, Cout, Cin, taps, grad);
+  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), dim3(32, 8), 0,
+                        static_cast<cudaStream_t>(stream)>>>(partial, splits, Cout, Cin, taps, grad);
   return static_cast<int>(cudaGetLastError());
 }
 

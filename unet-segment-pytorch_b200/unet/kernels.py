@@ -147,17 +147,21 @@ def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps):
     return out[0], out[1]
 
 
-def bn_act(y, scale, shift, relu=True, pool=False, write_act=True):
-    """a = relu(scale*y+shift) (and its 2x2 max-pooled copy)."""
+def bn_act(y, scale, shift, relu=True, pool=False, write_act=True, want_idx=False):
+    """a = relu(scale*y+shift), optionally its 2x2 max-pooled copy and the uint8 window position of
+    each maximum (saved for the backward pass)."""
     n, h, w, c, ld = _nhwc(y)
     a = empty_nhwc(n, h, w, c, y.device) if write_act else None
     p = empty_nhwc(n, h // 2, w // 2, c, y.device) if pool else None
-    _C.call("ub2_bn_act", ptr(y), ld, ptr(scale), ptr(shift), ptr(a), c, ptr(p), c, n, h, w, c,
+    idx = torch.empty((n, h // 2, w // 2, c), device=y.device, dtype=torch.uint8) if pool and want_idx else None
+    _C.call("ub2_bn_act", ptr(y), ld, ptr(scale), ptr(shift), ptr(a), c, ptr(p), c, ptr(idx), n, h, w, c,
             int(relu), stream())
+    if want_idx:
+        return a, p, idx
     return a, p
 
 
-def bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, relu=True, frozen=False):
+def bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, relu=True, frozen=False):
     """BatchNorm(+ReLU, + max-pool routing) backward: returns (dy bf16, dgamma, dbeta).
     ``frozen``: statistics were the running buffers (eval-mode backward), no mean terms."""
     n, h, w, c, ld_y = _nhwc(y)
@@ -166,12 +170,12 @@ def bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, relu=True, frozen=
     rows = _rows("ub2_bn_bwd_rows", n, h, w, c, int(dP is not None))
     dev = y.device
     partials = torch.empty((rows, 2, c), device=dev, dtype=F64)
-    _C.call("ub2_bn_bwd_reduce", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(y), ld_y, ptr(scale), ptr(shift),
-            ptr(partials), rows, n, h, w, c, int(relu), stream())
+    _C.call("ub2_bn_bwd_reduce", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(pidx), ptr(y), ld_y, ptr(scale),
+            ptr(shift), ptr(partials), rows, n, h, w, c, int(relu), stream())
     dgamma, dbeta, coef = bn_bwd_finalize(partials, n * h * w, gamma, mean, invstd, frozen)
     dy = empty_nhwc(n, h, w, c, dev)
-    _C.call("ub2_bn_bwd_apply", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(y), ld_y, ptr(scale), ptr(shift),
-            ptr(coef), ptr(dy), c, n, h, w, c, int(relu), stream())
+    _C.call("ub2_bn_bwd_apply", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(pidx), ptr(y), ld_y, ptr(scale),
+            ptr(shift), ptr(coef), ptr(dy), c, n, h, w, c, int(relu), stream())
     return dy, dgamma, dbeta
 
 
@@ -185,15 +189,15 @@ def bn_bwd_finalize(partials, count, gamma, mean, invstd, frozen=False):
     return grads[0], grads[1], coef
 
 
-def maxpool_bwd(dP, a):
-    """Route the pooled gradient to the first maximum of each 2x2 window of `a` (no BN, no ReLU)."""
+def maxpool_bwd(dP, pidx, a):
+    """Route the pooled gradient to the saved window positions (no BN, no ReLU)."""
     n, h, w, c, ld = _nhwc(a)
     dev = a.device
     ident = torch.zeros((5, c), device=dev, dtype=F32)
     ident[0].fill_(1.0)   # scale = 1
     ident[2].fill_(1.0)   # coef A = 1 (B = C = 0, shift = 0)
     dy = empty_nhwc(n, h, w, c, dev)
-    _C.call("ub2_bn_bwd_apply", ptr(None), 0, ptr(dP), _nhwc(dP)[4], ptr(a), ld, ptr(ident[0]),
+    _C.call("ub2_bn_bwd_apply", ptr(None), 0, ptr(dP), _nhwc(dP)[4], ptr(pidx), ptr(a), ld, ptr(ident[0]),
             ptr(ident[1]), ptr(ident[2]), ptr(dy), c, n, h, w, c, 0, stream())
     return dy
 

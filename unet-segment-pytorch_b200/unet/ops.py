@@ -78,20 +78,24 @@ class ConvBnRelu(torch.autograd.Function):
         else:
             y = K.conv_fwd(a0, wf, taps, x1=a1)
             scale, shift, mean, invstd = _bn_frozen_coeffs(bn)
-        a, p = K.bn_act(y, scale, shift, relu=True, pool=pool)
-        ctx.save_for_backward(a0, a1, y, scale, shift, mean, invstd, gamma, wd)
+        pidx = None
+        if pool:
+            a, p, pidx = K.bn_act(y, scale, shift, relu=True, pool=True, want_idx=True)
+        else:
+            a, p = K.bn_act(y, scale, shift, relu=True, pool=False)
+        ctx.save_for_backward(a0, a1, y, scale, shift, mean, invstd, gamma, wd, pidx)
         ctx.meta = (weight.shape, batch)
         return from_nhwc(a), (from_nhwc(p) if pool else None)
 
     @staticmethod
     def backward(ctx, dA, dP):
-        a0, a1, y, scale, shift, mean, invstd, gamma, wd = ctx.saved_tensors
+        a0, a1, y, scale, shift, mean, invstd, gamma, wd, pidx = ctx.saved_tensors
         wshape, batch = ctx.meta
         cout, cin, kh, kw = wshape
         taps = kh * kw
         dA_n = to_nhwc(dA) if dA is not None else None
         dP_n = to_nhwc(dP) if dP is not None else None
-        dy, dgamma, dbeta = _bn_backward(dA_n, dP_n, y, scale, shift, mean, invstd, gamma, batch)
+        dy, dgamma, dbeta = _bn_backward(dA_n, dP_n, pidx, y, scale, shift, mean, invstd, gamma, batch)
         gw = None
         if ctx.needs_input_grad[2]:
             part = K.conv_wgrad(a0, dy, taps, x1=a1)
@@ -109,8 +113,8 @@ class ConvBnRelu(torch.autograd.Function):
         return d0, d1, gw, dgamma, dbeta, None, None
 
 
-def _bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, batch, relu=True):
-    return K.bn_backward(dA, dP, y, scale, shift, mean, invstd, gamma, relu=relu, frozen=not batch)
+def _bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, batch, relu=True):
+    return K.bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, relu=relu, frozen=not batch)
 
 
 class ConvInBnRelu(torch.autograd.Function):
@@ -140,7 +144,7 @@ class ConvInBnRelu(torch.autograd.Function):
     def backward(ctx, dA):
         x, y, scale, shift, mean, invstd, gamma = ctx.saved_tensors
         wshape, batch = ctx.meta
-        dy, dgamma, dbeta = _bn_backward(to_nhwc(dA), None, y, scale, shift, mean, invstd, gamma, batch)
+        dy, dgamma, dbeta = _bn_backward(to_nhwc(dA), None, None, y, scale, shift, mean, invstd, gamma, batch)
         gw = K.conv_in_wgrad(x, dy, wshape[0])
         return None, gw, dgamma, dbeta, None
 
@@ -270,13 +274,14 @@ class MaxPool2x2(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         a = to_nhwc(x)
-        ctx.save_for_backward(a)
-        return from_nhwc(K.bn_act(a, None, None, relu=False, pool=True, write_act=False)[1])
+        _, p, pidx = K.bn_act(a, None, None, relu=False, pool=True, write_act=False, want_idx=True)
+        ctx.save_for_backward(a, pidx)
+        return from_nhwc(p)
 
     @staticmethod
     def backward(ctx, dp):
-        (a,) = ctx.saved_tensors
-        return from_nhwc(K.maxpool_bwd(to_nhwc(dp), a))
+        a, pidx = ctx.saved_tensors
+        return from_nhwc(K.maxpool_bwd(to_nhwc(dp), pidx, a))
 
 
 class ConvFn(torch.autograd.Function):
