@@ -110,6 +110,12 @@ WG_CASES = [
     (1, 8, 8, 16, 16, 48, 9),
     (2, 32, 32, 256, 0, 512, 9),
     (4, 64, 64, 64, 0, 64, 9),
+    # wide rows: halo-resident wgrad kernel
+    (2, 5, 128, 64, 64, 64, 9),
+    (1, 7, 256, 128, 0, 128, 9),    # two tap groups
+    (3, 9, 128, 64, 0, 32, 9),
+    (1, 4, 128, 64, 0, 96, 9),
+    (2, 16, 512, 64, 0, 64, 9),
 ]
 
 

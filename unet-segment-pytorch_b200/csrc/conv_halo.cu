@@ -30,7 +30,11 @@ struct HaloSmemHeader {
 };
 
 static int g_conv_mode = 0;
-void conv_set_mode(int mode) { g_conv_mode = mode; }
+int g_conv_mode_wgrad = 0;
+void conv_set_mode(int mode) {
+  g_conv_mode = mode;
+  g_conv_mode_wgrad = mode;
+}
 
 template <bool ACC>
 __global__ void __launch_bounds__(kHThreads, 1)

@@ -225,7 +225,14 @@ static int pow2_floor_w(int x) {
   return r;
 }
 
+int conv_wgrad_halo_launch(const ConvWgradArgs& a, cudaStream_t stream);
+extern int g_conv_mode_wgrad;
+
 int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
+  if (g_conv_mode_wgrad != 1) {
+    const int rc = conv_wgrad_halo_launch(a, stream);
+    if (rc != 1) return rc;
+  }
   const int Ctot = a.C0 + a.C1;
   if (a.taps != 1 && a.taps != 9) return UB2_ERR_SHAPE;
   if (a.N <= 0 || a.H <= 0 || a.W <= 0 || a.C0 <= 0 || a.C1 < 0) return UB2_ERR_SHAPE;
