@@ -143,18 +143,17 @@ int ub2_gate_bwd_a(const void* dout, int ld_do, const void* x, int ld_x, const f
                    int N, int H, int W, int Cx, void* stream);
 int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_psi, const void* q,
                    int ld_q, const void* xp, int ld_xp, const float* scale_g, const float* shift_g,
-                   const float* scale_x, const float* shift_x, const float* mean_g,
-                   const float* invstd_g, const float* mean_x, const float* invstd_x,
-                   const float* wpsi, void* ds, int ld_ds, double* partials, int rows, int N, int hin,
-                   int win, int H, int W, int Ci, void* stream);
+                   const float* scale_x, const float* shift_x, const float* wpsi, void* ds, int ld_ds,
+                   double* partials, int rows, int N, int hin, int win, int H, int W, int Ci,
+                   void* stream);
 int ub2_gate_bwd_finalize(const double* partials, int rows, int Ci, double count, const float* gamma_x,
-                          const float* invstd_x, const float* gamma_g, const float* invstd_g,
-                          int frozen, float* dgamma_x, float* dbeta_x, float* dgamma_g, float* dbeta_g,
-                          float* dwpsi, float* coef, void* stream);
+                          const float* mean_x, const float* invstd_x, const float* gamma_g,
+                          const float* mean_g, const float* invstd_g, int frozen, float* dgamma_x,
+                          float* dbeta_x, float* dgamma_g, float* dbeta_g, float* dwpsi, float* coef,
+                          void* stream);
 int ub2_gate_bwd_xg(const void* ds, int ld_ds, const void* xp, int ld_xp, const void* q, int ld_q,
-                    const float* mean_x, const float* invstd_x, const float* mean_g,
-                    const float* invstd_g, const float* coef, void* dxp, int ld_dxp, void* dgup,
-                    int ld_dg, int N, int hin, int win, int H, int W, int Ci, void* stream);
+                    const float* coef, void* dxp, int ld_dxp, void* dgup, int ld_dg, int N, int hin,
+                    int win, int H, int W, int Ci, void* stream);
 
 /* ======================= network ends =================================================== */
 

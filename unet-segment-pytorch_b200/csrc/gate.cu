@@ -146,6 +146,25 @@ gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* parti
   block_reduce_channels<G, 2>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 2 * g.C, smem);
 }
 
+// Per-channel coefficient vectors of the thread's first channel group, kept in registers
+// (the thread -> channel-group mapping is fixed); further groups (Ci > 256) read through L1.
+struct GateVec {
+  F8 sg, sx, h, w;
+};
+__device__ __forceinline__ GateVec gate_vec(const float* sg, const float* hg, const float* sx,
+                                            const float* hx, const float* wpsi, int cg, int cgs) {
+  GateVec v;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = (cg < cgs ? cg : 0) * 8 + k;
+    v.sg.v[k] = __ldg(sg + c);
+    v.sx.v[k] = __ldg(sx + c);
+    v.h.v[k] = __ldg(hg + c) + __ldg(hx + c);
+    v.w.v[k] = __ldg(wpsi + c);
+  }
+  return v;
+}
+
 template <int G>
 __global__ void __launch_bounds__(kGateThreads)
 gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat16* __restrict__ xp,
@@ -155,6 +174,7 @@ gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat
                 GateGeom g) {
   __shared__ float smem[kGateThreads / 32];
   float st[2] = {0.f, 0.f};
+  const GateVec v0 = gate_vec(sg, hg, sx, hx, wpsi, threadIdx.x % g.tpp, g.cgs);
   GATE_PIXEL_LOOP(g) {
     GATE_PIX(g)
     GATE_DECODE(g)
@@ -163,13 +183,13 @@ gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat
     for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
+        const GateVec v = (gi == 0) ? v0 : gate_vec(sg, hg, sx, hx, wpsi, cg, g.cgs);
         const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
         const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int c = cg * 8 + k;
-          const float t = fmaf(u.v[k], __ldg(sg + c), __ldg(hg + c)) + fmaf(xv.v[k], __ldg(sx + c), __ldg(hx + c));
-          dot = fmaf(__ldg(wpsi + c), fmaxf(t, 0.f), dot);
+          const float t = fmaf(u.v[k], v.sg.v[k], fmaf(xv.v[k], v.sx.v[k], v.h.v[k]));
+          dot = fmaf(v.w.v[k], fmaxf(t, 0.f), dot);
         }
       }
     }
@@ -243,19 +263,19 @@ gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_
   block_reduce_scalars<2>(st, partials + static_cast<size_t>(blockIdx.x) * 2, smem);
 }
 
-// ds_c = dpsi_raw * w_psi_c * [t_c > 0]; channel sums: ds, ds*xhat_x, ds*xhat_g, dpsi_raw*relu(t)
+// ds_c = dpsi_raw * w_psi_c * [t_c > 0]; channel sums (raw, the finalize converts them):
+// sum ds, sum ds*xp, sum ds*up(q), sum dpsi_raw*relu(t)
 template <int G>
 __global__ void __launch_bounds__(kGateThreads)
 gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi_raw,
                   const float* __restrict__ coef_psi, const __nv_bfloat16* __restrict__ q, int ld_q,
                   const __nv_bfloat16* __restrict__ xp, int ld_xp, const float* __restrict__ sg,
                   const float* __restrict__ hg, const float* __restrict__ sx,
-                  const float* __restrict__ hx, const float* __restrict__ mean_g,
-                  const float* __restrict__ invstd_g, const float* __restrict__ mean_x,
-                  const float* __restrict__ invstd_x, const float* __restrict__ wpsi,
+                  const float* __restrict__ hx, const float* __restrict__ wpsi,
                   __nv_bfloat16* __restrict__ ds, int ld_ds, double* partials, GateGeom g) {
   __shared__ float smem[kGateThreads * 8];
   const float cA = __ldg(coef_psi), cB = __ldg(coef_psi + 1), cC = __ldg(coef_psi + 2);
+  const GateVec v0 = gate_vec(sg, hg, sx, hx, wpsi, threadIdx.x % g.tpp, g.cgs);
   float acc[G][4][8];
 #pragma unroll
   for (int a = 0; a < G; ++a)
@@ -272,18 +292,18 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
     for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
+        const GateVec v = (gi == 0) ? v0 : gate_vec(sg, hg, sx, hx, wpsi, cg, g.cgs);
         const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
         const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
         F8 o;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int c = cg * 8 + k;
-          const float t = fmaf(u.v[k], __ldg(sg + c), __ldg(hg + c)) + fmaf(xv.v[k], __ldg(sx + c), __ldg(hx + c));
-          const float d = (t > 0.f) ? dpr * __ldg(wpsi + c) : 0.f;
+          const float t = fmaf(u.v[k], v.sg.v[k], fmaf(xv.v[k], v.sx.v[k], v.h.v[k]));
+          const float d = (t > 0.f) ? dpr * v.w.v[k] : 0.f;
           o.v[k] = d;
           acc[gi][0][k] += d;
-          acc[gi][1][k] = fmaf(d, (xv.v[k] - __ldg(mean_x + c)) * __ldg(invstd_x + c), acc[gi][1][k]);
-          acc[gi][2][k] = fmaf(d, (u.v[k] - __ldg(mean_g + c)) * __ldg(invstd_g + c), acc[gi][2][k]);
+          acc[gi][1][k] = fmaf(d, xv.v[k], acc[gi][1][k]);
+          acc[gi][2][k] = fmaf(d, u.v[k], acc[gi][2][k]);
           acc[gi][3][k] = fmaf(dpr, fmaxf(t, 0.f), acc[gi][3][k]);
         }
         store8(ds + static_cast<size_t>(pix) * ld_ds + cg * 8, o);
@@ -294,12 +314,15 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
   block_reduce_channels<G, 4>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 4 * g.C, smem);
 }
 
-// coef rows: 0..2 = BN_x {gamma*invstd, sum(ds)/M, sum(ds*xhat_x)/M}; 3..5 = BN_g
+// Raw sums -> parameter gradients and the backward coefficients of the two BatchNorms:
+//   dxp = coef0*ds + coef1*xp + coef2 ;  d(up q) = coef3*ds + coef4*up(q) + coef5
 // blockDim = (32, 32): see rows_sum in vec.cuh
 __global__ void gate_bwd_finalize_kernel(const double* __restrict__ partials, int rows, int C,
                                          double count, const float* __restrict__ gamma_x,
+                                         const float* __restrict__ mean_x,
                                          const float* __restrict__ invstd_x,
                                          const float* __restrict__ gamma_g,
+                                         const float* __restrict__ mean_g,
                                          const float* __restrict__ invstd_g, int frozen, float* dgamma_x,
                                          float* dbeta_x, float* dgamma_g, float* dbeta_g, float* dwpsi,
                                          float* coef) {
@@ -308,48 +331,68 @@ __global__ void gate_bwd_finalize_kernel(const double* __restrict__ partials, in
   double s[4];
   rows_sum<4>(partials, rows, C, c, s, smem);
   if (threadIdx.y != 0 || c >= C) return;
-  if (dbeta_x) dbeta_x[c] += static_cast<float>(s[0]);
-  if (dgamma_x) dgamma_x[c] += static_cast<float>(s[1]);
-  if (dbeta_g) dbeta_g[c] += static_cast<float>(s[0]);
-  if (dgamma_g) dgamma_g[c] += static_cast<float>(s[2]);
+  const double mx = mean_x[c], ix = invstd_x[c], mg = mean_g[c], ig = invstd_g[c];
+  const double db = s[0];
+  const double dgx = ix * (s[1] - mx * s[0]);
+  const double dgg = ig * (s[2] - mg * s[0]);
+  if (dbeta_x) dbeta_x[c] += static_cast<float>(db);
+  if (dgamma_x) dgamma_x[c] += static_cast<float>(dgx);
+  if (dbeta_g) dbeta_g[c] += static_cast<float>(db);
+  if (dgamma_g) dgamma_g[c] += static_cast<float>(dgg);
   if (dwpsi) dwpsi[c] += static_cast<float>(s[3]);
-  const double inv_m = frozen ? 0.0 : 1.0 / count;
-  coef[0 * C + c] = gamma_x[c] * invstd_x[c];
-  coef[1 * C + c] = static_cast<float>(s[0] * inv_m);
-  coef[2 * C + c] = static_cast<float>(s[1] * inv_m);
-  coef[3 * C + c] = gamma_g[c] * invstd_g[c];
-  coef[4 * C + c] = static_cast<float>(s[0] * inv_m);
-  coef[5 * C + c] = static_cast<float>(s[2] * inv_m);
+  const double Ax = gamma_x[c] * ix, Ag = gamma_g[c] * ig;
+  const double Bx = frozen ? 0.0 : -Ax * ix * dgx / count;
+  const double Bg = frozen ? 0.0 : -Ag * ig * dgg / count;
+  coef[0 * C + c] = static_cast<float>(Ax);
+  coef[1 * C + c] = static_cast<float>(Bx);
+  coef[2 * C + c] = static_cast<float>(frozen ? 0.0 : -Ax * db / count - Bx * mx);
+  coef[3 * C + c] = static_cast<float>(Ag);
+  coef[4 * C + c] = static_cast<float>(Bg);
+  coef[5 * C + c] = static_cast<float>(frozen ? 0.0 : -Ag * db / count - Bg * mg);
 }
 
 // dxp = BN_x backward of ds; dgup = BN_g backward of ds (full resolution, later up-sample^T)
-__global__ void __launch_bounds__(256)
+template <int G>
+__global__ void __launch_bounds__(kGateThreads)
 gate_bwd_xg_kernel(const __nv_bfloat16* __restrict__ ds, int ld_ds, const __nv_bfloat16* __restrict__ xp,
                    int ld_xp, const __nv_bfloat16* __restrict__ q, int ld_q,
-                   const float* __restrict__ mean_x, const float* __restrict__ invstd_x,
-                   const float* __restrict__ mean_g, const float* __restrict__ invstd_g,
                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dxp, int ld_dxp,
                    __nv_bfloat16* __restrict__ dgup, int ld_dg, GateGeom g) {
-  const int total = g.pixels * g.cgs;
-  for (int i = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % g.cgs);
-    const int pix = i / g.cgs;
-    GATE_DECODE(g)
-    const F8 d = load8_stream(ds + static_cast<size_t>(pix) * ld_ds + cg * 8);
-    const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
-    const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
-    F8 ox, og;
+  F8 cf[6];
+  {
+    const int cg0 = threadIdx.x % g.tpp;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = cg * 8 + k;
-      const float xh = (xv.v[k] - __ldg(mean_x + c)) * __ldg(invstd_x + c);
-      const float gh = (u.v[k] - __ldg(mean_g + c)) * __ldg(invstd_g + c);
-      ox.v[k] = __ldg(coef + c) * (d.v[k] - __ldg(coef + g.C + c) - xh * __ldg(coef + 2 * g.C + c));
-      og.v[k] = __ldg(coef + 3 * g.C + c) * (d.v[k] - __ldg(coef + 4 * g.C + c) - gh * __ldg(coef + 5 * g.C + c));
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cf[r].v[k] = __ldg(coef + r * g.C + (cg0 < g.cgs ? cg0 : 0) * 8 + k);
+  }
+  GATE_PIXEL_LOOP(g) {
+    GATE_PIX(g)
+    GATE_DECODE(g)
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+      const int cg = j + gi * g.tpp;
+      if (pv && cg < g.cgs) {
+        const F8 d = load8_stream(ds + static_cast<size_t>(pix) * ld_ds + cg * 8);
+        const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
+        const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
+        F8 ox, og;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (gi == 0) {
+            ox.v[k] = fmaf(cf[0].v[k], d.v[k], fmaf(cf[1].v[k], xv.v[k], cf[2].v[k]));
+            og.v[k] = fmaf(cf[3].v[k], d.v[k], fmaf(cf[4].v[k], u.v[k], cf[5].v[k]));
+          } else {
+            const int c = cg * 8 + k;
+            ox.v[k] = fmaf(__ldg(coef + c), d.v[k], fmaf(__ldg(coef + g.C + c), xv.v[k], __ldg(coef + 2 * g.C + c)));
+            og.v[k] = fmaf(__ldg(coef + 3 * g.C + c), d.v[k],
+                           fmaf(__ldg(coef + 4 * g.C + c), u.v[k], __ldg(coef + 5 * g.C + c)));
+          }
+        }
+        store8(dxp + static_cast<size_t>(pix) * ld_dxp + cg * 8, ox);
+        store8(dgup + static_cast<size_t>(pix) * ld_dg + cg * 8, og);
+      }
     }
-    store8(dxp + static_cast<size_t>(pix) * ld_dxp + cg * 8, ox);
-    store8(dgup + static_cast<size_t>(pix) * ld_dg + cg * 8, og);
   }
 }
 
@@ -434,12 +477,10 @@ int ub2_gate_bwd_a(const void* dout, int ld_do, const void* x, int ld_x, const f
 }
 
 int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_psi, const void* q,
-                   int ld_q,
-                   const void* xp, int ld_xp, const float* scale_g, const float* shift_g,
-                   const float* scale_x, const float* shift_x, const float* mean_g,
-                   const float* invstd_g, const float* mean_x, const float* invstd_x,
-                   const float* wpsi, void* ds, int ld_ds, double* partials, int rows, int N, int hin,
-                   int win, int H, int W, int Ci, void* stream) {
+                   int ld_q, const void* xp, int ld_xp, const float* scale_g, const float* shift_g,
+                   const float* scale_x, const float* shift_x, const float* wpsi, void* ds, int ld_ds,
+                   double* partials, int rows, int N, int hin, int win, int H, int W, int Ci,
+                   void* stream) {
   GateGeom g;
   int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
   if (rc) return rc;
@@ -448,36 +489,42 @@ int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_p
   if (g.cgs > g.tpp)
     gate_bwd_s_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g,
-        scale_x, shift_x, mean_g, invstd_g, mean_x, invstd_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
+        scale_x, shift_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
   else
     gate_bwd_s_kernel<1><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g,
-        scale_x, shift_x, mean_g, invstd_g, mean_x, invstd_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
+        scale_x, shift_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_gate_bwd_finalize(const double* partials, int rows, int Ci, double count, const float* gamma_x,
-                          const float* invstd_x, const float* gamma_g, const float* invstd_g,
-                          int frozen, float* dgamma_x, float* dbeta_x, float* dgamma_g, float* dbeta_g,
-                          float* dwpsi, float* coef, void* stream) {
+                          const float* mean_x, const float* invstd_x, const float* gamma_g,
+                          const float* mean_g, const float* invstd_g, int frozen, float* dgamma_x,
+                          float* dbeta_x, float* dgamma_g, float* dbeta_g, float* dwpsi, float* coef,
+                          void* stream) {
   if (Ci <= 0 || rows <= 0) return UB2_ERR_SHAPE;
   gate_bwd_finalize_kernel<<<(Ci + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
-      partials, rows, Ci, count, gamma_x, invstd_x, gamma_g, invstd_g, frozen, dgamma_x, dbeta_x,
-      dgamma_g, dbeta_g, dwpsi, coef);
+      partials, rows, Ci, count, gamma_x, mean_x, invstd_x, gamma_g, mean_g, invstd_g, frozen, dgamma_x,
+      dbeta_x, dgamma_g, dbeta_g, dwpsi, coef);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_gate_bwd_xg(const void* ds, int ld_ds, const void* xp, int ld_xp, const void* q, int ld_q,
-                    const float* mean_x, const float* invstd_x, const float* mean_g,
-                    const float* invstd_g, const float* coef, void* dxp, int ld_dxp, void* dgup,
-                    int ld_dg, int N, int hin, int win, int H, int W, int Ci, void* stream) {
+                    const float* coef, void* dxp, int ld_dxp, void* dgup, int ld_dg, int N, int hin,
+                    int win, int H, int W, int Ci, void* stream) {
   GateGeom g;
   int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
   if (rc) return rc;
-  gate_bwd_xg_kernel<<<stream_grid(g.pixels * g.cgs, 256, num_sms()), 256, 0,
-                       static_cast<cudaStream_t>(stream)>>>(
-      static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp, static_cast<cbf>(q), ld_q, mean_x,
-      invstd_x, mean_g, invstd_g, coef, static_cast<bf>(dxp), ld_dxp, static_cast<bf>(dgup), ld_dg, g);
+  const int grid = gate_grid(g, 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g.cgs > g.tpp)
+    gate_bwd_xg_kernel<2><<<grid, kGateThreads, 0, s>>>(static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp,
+                                                        static_cast<cbf>(q), ld_q, coef, static_cast<bf>(dxp),
+                                                        ld_dxp, static_cast<bf>(dgup), ld_dg, g);
+  else
+    gate_bwd_xg_kernel<1><<<grid, kGateThreads, 0, s>>>(static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp,
+                                                        static_cast<cbf>(q), ld_q, coef, static_cast<bf>(dxp),
+                                                        ld_dxp, static_cast<bf>(dgup), ld_dg, g);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -101,6 +101,83 @@ conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __n
   }
 }
 
+// Cin == 1, W % 4 == 0: a thread owns 4 consecutive pixels x 8 channels; its 72 weights and the
+// 3x6 input window live in registers (288 FMAs per 18 loads and 4 stores).
+__global__ void __launch_bounds__(kHeadThreads)
+conv_in_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                    int ld_y, double* partials, int N, int H, int W, int Cout) {
+  extern __shared__ float s_red[];  // [lanes][cgs][16]
+  const int cgs = Cout / 8;
+  const int lanes = blockDim.x / cgs;
+  const int lane = threadIdx.x / cgs, cg = threadIdx.x % cgs;
+  const bool active = lane < lanes;
+  const int rows = N * H;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[t][k] = __ldg(w + (cg * 8 + k) * 9 + t);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s1[k] = s2[k] = 0.f;
+  if (active) {
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int hq = row % H;
+      const float* xrow = x + static_cast<size_t>(row) * W;
+      for (int wq = lane * 4; wq < W; wq += lanes * 4) {
+        float xv[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int hh = hq + r - 1;
+          const bool rv = hh >= 0 && hh < H;
+          const float* xp = xrow + (r - 1) * W + wq;
+          xv[r][0] = (rv && wq > 0) ? __ldg(xp - 1) : 0.f;
+          const float4 mid = rv ? __ldg(reinterpret_cast<const float4*>(xp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xv[r][1] = mid.x; xv[r][2] = mid.y; xv[r][3] = mid.z; xv[r][4] = mid.w;
+          xv[r][5] = (rv && wq + 4 < W) ? __ldg(xp + 4) : 0.f;
+        }
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          float acc[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv[r][px + s], wr[r * 3 + s][k], acc[k]);
+          F8 o;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
+          const uint4 packed = pack8(o);
+          *reinterpret_cast<uint4*>(y + (static_cast<size_t>(row) * W + wq + px) * ld_y + cg * 8) = packed;
+          const F8 rr = unpack8(packed);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            s1[k] += rr.v[k];
+            s2[k] = fmaf(rr.v[k], rr.v[k], s2[k]);
+          }
+        }
+      }
+    }
+  }
+  if (partials != nullptr) {
+    float* mine = s_red + (static_cast<size_t>(lane) * cgs + cg) * 16;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { mine[k] = s1[k]; mine[8 + k] = s2[k]; }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cgs * 16; idx += blockDim.x) {
+      double a = 0.0;
+      for (int l = 0; l < lanes; ++l) a += static_cast<double>(s_red[static_cast<size_t>(l) * cgs * 16 + idx]);
+      const int cgi = idx / 16, k = idx % 16;
+      partials[(static_cast<size_t>(blockIdx.x) * 2 + (k >> 3)) * Cout + cgi * 8 + (k & 7)] = a;
+    }
+  }
+}
+
 // dW[co][ci][t] = sum_p dy[p][co] * x[p + shift_t][ci]; blockIdx.y = ci; rows of [9][Cout] doubles
 __global__ void __launch_bounds__(kHeadThreads)
 conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int ld_dy,
@@ -171,48 +248,67 @@ struct HeadGeom {
   int pixels, HW;
 };
 
+// KMAX >= n_classes.  `tpp` threads share a pixel (8 channels each, C <= 256: one group per
+// thread, its weights in registers); 4 pixels per trip keep 4 independent 128-bit loads in flight.
+template <int KMAX>
 __global__ void __launch_bounds__(kHeadThreads)
 outc_fwd_kernel(const __nv_bfloat16* __restrict__ a, int ld_a, const float* __restrict__ w,
                 const float* __restrict__ bias, float* __restrict__ logits, HeadGeom g) {
   const int slot = threadIdx.x / g.tpp, j = threadIdx.x % g.tpp;
-  // one channel group per thread (C <= 256): its weights stay in registers
   const bool single = g.cgs <= g.tpp;
-  F8 wreg[kMaxClasses];
+  F8 wreg[KMAX];
+  float breg[KMAX];
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
-    if (single && k < g.K && j < g.cgs) wreg[k] = loadf8(w + static_cast<size_t>(k) * g.C + j * 8);
+  for (int k = 0; k < KMAX; ++k) {
+    breg[k] = (bias != nullptr && k < g.K) ? __ldg(bias + k) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      wreg[k].v[i] = (single && k < g.K && j < g.cgs) ? __ldg(w + static_cast<size_t>(k) * g.C + j * 8 + i) : 0.f;
   }
-  for (int base = static_cast<int>(blockIdx.x) * g.slots; base < g.pixels;
-       base += static_cast<int>(gridDim.x) * g.slots) {
-    const int pix = base + slot;
-    const bool pv = pix < g.pixels;
-    float dot[kMaxClasses];
+  const int stride = static_cast<int>(gridDim.x) * g.slots;
+  for (int base = static_cast<int>(blockIdx.x) * g.slots; base < g.pixels; base += 4 * stride) {
+    float dot[4][KMAX];
+    F8 v[4];
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) dot[k] = 0.f;
-    for (int cg = j; cg < g.cgs; cg += g.tpp) {
-      if (pv) {
-        const F8 v = load8_stream(a + static_cast<size_t>(pix) * ld_a + cg * 8);
+    for (int u = 0; u < 4; ++u) {
+      const int pix = base + u * stride + slot;
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) {
-          if (k < g.K) {
-            const F8 wv = single ? wreg[k] : loadf8(w + static_cast<size_t>(k) * g.C + cg * 8);
+      for (int i = 0; i < 8; ++i) v[u].v[i] = 0.f;
+      if (single && pix < g.pixels && j < g.cgs) v[u] = load8_stream(a + static_cast<size_t>(pix) * ld_a + j * 8);
+    }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dot[k] = fmaf(v.v[i], wv.v[i], dot[k]);
+    for (int u = 0; u < 4; ++u) {
+      const int pix = base + u * stride + slot;
+      const bool pv = pix < g.pixels;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) dot[u][k] = 0.f;
+      if (single) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dot[u][k] = fmaf(v[u].v[i], wreg[k].v[i], dot[u][k]);
+      } else if (pv) {
+        for (int cg = j; cg < g.cgs; cg += g.tpp) {
+          const F8 vv = load8_stream(a + static_cast<size_t>(pix) * ld_a + cg * 8);
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (k < g.K) {
+              const F8 wv = loadf8(w + static_cast<size_t>(k) * g.C + cg * 8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dot[u][k] = fmaf(vv.v[i], wv.v[i], dot[u][k]);
+            }
           }
         }
       }
-    }
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
-      if (k < g.K) {
-        for (int o = g.tpp >> 1; o > 0; o >>= 1) dot[k] += __shfl_xor_sync(0xffffffffu, dot[k], o);
+      for (int k = 0; k < KMAX; ++k)
+        for (int o = g.tpp >> 1; o > 0; o >>= 1) dot[u][k] += __shfl_xor_sync(0xffffffffu, dot[u][k], o);
+      if (pv && j == 0) {
+        const int n = pix / g.HW, r = pix % g.HW;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < g.K) logits[(static_cast<size_t>(n) * g.K + k) * g.HW + r] = dot[u][k] + breg[k];
       }
-    }
-    if (pv && j == 0) {
-      const int n = pix / g.HW, r = pix % g.HW;
-#pragma unroll
-      for (int k = 0; k < kMaxClasses; ++k)
-        if (k < g.K) logits[(n * g.K + k) * g.HW + r] = dot[k] + (bias ? __ldg(bias + k) : 0.f);
     }
   }
 }
@@ -358,7 +454,11 @@ int ub2_conv_in_fwd(const float* x, const float* w, void* y, int ld_y, double* p
   const int grid = stream_grid(static_cast<int>(N) * H * W, lanes, num_sms(), 4);
   if (partials != nullptr && grid != rows) return UB2_ERR_WORKSPACE;
   const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + static_cast<size_t>(lanes) * cgs * 16) * sizeof(float);
-  if (Cin == 1)
+  if (Cin == 1 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    conv_in_fwd4_kernel<<<grid, block, static_cast<size_t>(lanes) * cgs * 16 * sizeof(float),
+                          static_cast<cudaStream_t>(stream)>>>(x, w, static_cast<__nv_bfloat16*>(y), ld_y,
+                                                               partials, N, H, W, Cout);
+  else if (Cin == 1)
     conv_in_fwd_kernel<true><<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
         x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, Cin, H, W, Cout);
   else
@@ -397,9 +497,12 @@ int ub2_outc_fwd(const void* a, int ld_a, const float* w, const float* bias, flo
   HeadGeom g;
   int rc = head_geom(&g, N, H, W, C, K);
   if (rc) return rc;
-  outc_fwd_kernel<<<stream_grid(g.pixels, g.slots, num_sms(), 8), kHeadThreads, 0,
-                    static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(a), ld_a, w,
-                                                        bias, logits, g);
+  const int grid = stream_grid((g.pixels + 3) / 4, g.slots, num_sms(), 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(a);
+  if (K <= 2) outc_fwd_kernel<2><<<grid, kHeadThreads, 0, s>>>(ap, ld_a, w, bias, logits, g);
+  else if (K <= 4) outc_fwd_kernel<4><<<grid, kHeadThreads, 0, s>>>(ap, ld_a, w, bias, logits, g);
+  else outc_fwd_kernel<8><<<grid, kHeadThreads, 0, s>>>(ap, ld_a, w, bias, logits, g);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -264,37 +264,37 @@ def gate_bwd_a(dout, x, a, psi):
     return dx, dpsin, partials
 
 
-def gate_bwd_s(dpsin, psi, coef_psi, q, xp, sg, hg, sx, hx, mean_g, invstd_g, mean_x, invstd_x, wpsi):
+def gate_bwd_s(dpsin, psi, coef_psi, q, xp, sg, hg, sx, hx, wpsi):
     n, hin, win, ci, ld_q = _nhwc(q)
     _, h, w, _, ld_xp = _nhwc(xp)
     ds = empty_nhwc(n, h, w, ci, q.device)
     rows = gate_rows(n, h, w, ci)
     partials = torch.empty((rows, 4, ci), device=q.device, dtype=F64)
     _C.call("ub2_gate_bwd_s", ptr(dpsin), ptr(psi), ptr(coef_psi), ptr(q), ld_q, ptr(xp), ld_xp, ptr(sg),
-            ptr(hg), ptr(sx), ptr(hx), ptr(mean_g), ptr(invstd_g), ptr(mean_x), ptr(invstd_x), ptr(wpsi),
-            ptr(ds), ci, ptr(partials), rows, n, hin, win, h, w, ci, stream())
+            ptr(hg), ptr(sx), ptr(hx), ptr(wpsi), ptr(ds), ci, ptr(partials), rows, n, hin, win, h, w, ci,
+            stream())
     return ds, partials
 
 
-def gate_bwd_finalize(partials, count, gamma_x, invstd_x, gamma_g, invstd_g, frozen=False):
+def gate_bwd_finalize(partials, count, gamma_x, mean_x, invstd_x, gamma_g, mean_g, invstd_g, frozen=False):
     rows, _, ci = partials.shape
     grads = torch.zeros((5, ci), device=partials.device, dtype=F32)
     coef = torch.empty((6, ci), device=partials.device, dtype=F32)
     _C.call("ub2_gate_bwd_finalize", ptr(partials), rows, ci, c_double(float(count)), ptr(gamma_x),
-            ptr(invstd_x), ptr(gamma_g), ptr(invstd_g), int(frozen), ptr(grads[0]), ptr(grads[1]),
+            ptr(mean_x), ptr(invstd_x), ptr(gamma_g), ptr(mean_g), ptr(invstd_g), int(frozen), ptr(grads[0]),
+            ptr(grads[1]),
             ptr(grads[2]), ptr(grads[3]), ptr(grads[4]), ptr(coef), stream())
     # dgamma_x, dbeta_x, dgamma_g, dbeta_g, dwpsi
     return grads, coef
 
 
-def gate_bwd_xg(ds, xp, q, mean_x, invstd_x, mean_g, invstd_g, coef):
+def gate_bwd_xg(ds, xp, q, coef):
     n, hin, win, ci, ld_q = _nhwc(q)
     _, h, w, _, ld_xp = _nhwc(xp)
     dxp = empty_nhwc(n, h, w, ci, q.device)
     dgup = empty_nhwc(n, h, w, ci, q.device)
-    _C.call("ub2_gate_bwd_xg", ptr(ds), _nhwc(ds)[4], ptr(xp), ld_xp, ptr(q), ld_q, ptr(mean_x),
-            ptr(invstd_x), ptr(mean_g), ptr(invstd_g), ptr(coef), ptr(dxp), ci, ptr(dgup), ci, n, hin,
-            win, h, w, ci, stream())
+    _C.call("ub2_gate_bwd_xg", ptr(ds), _nhwc(ds)[4], ptr(xp), ld_xp, ptr(q), ld_q, ptr(coef), ptr(dxp), ci,
+            ptr(dgup), ci, n, hin, win, h, w, ci, stream())
     return dxp, dgup
 
 

@@ -213,9 +213,9 @@ class AttentionGateFn(torch.autograd.Function):
         d = to_nhwc(dout)
         dx, dpsin, part = K.gate_bwd_a(d, xn, a, psi)
         dgam_p, dbet_p, coef_p = K.bn_bwd_finalize(part, count, gam_p, mp, ip, frozen=not batch)
-        ds, part2 = K.gate_bwd_s(dpsin, psi, coef_p, q, xp, sg, hg, sx, hx, mg, ig, mx, ix, wpsi)
-        grads, coef = K.gate_bwd_finalize(part2, count, gam_x, ix, gam_g, ig, frozen=not batch)
-        dxp, dgup = K.gate_bwd_xg(ds, xp, q, mx, ix, mg, ig, coef)
+        ds, part2 = K.gate_bwd_s(dpsin, psi, coef_p, q, xp, sg, hg, sx, hx, wpsi)
+        grads, coef = K.gate_bwd_finalize(part2, count, gam_x, mx, ix, gam_g, mg, ig, frozen=not batch)
+        dxp, dgup = K.gate_bwd_xg(ds, xp, q, coef)
         dq = K.upsample_bwd(dgup, hin, win, h, w)
         gw_x = torch.zeros(sh_x, device=d.device, dtype=torch.float32)
         K.wgrad_reduce(K.conv_wgrad(xn, dxp, 1), ci, cx, 1, gw_x)
