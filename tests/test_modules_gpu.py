@@ -262,3 +262,26 @@ def test_cpu_tensor_raises():
     from unet.models import UNet
     with pytest.raises(RuntimeError, match="CUDA"):
         UNet(base_features=16)(torch.zeros(1, 1, 32, 32))
+
+
+def test_cuda_graph_step_equals_eager():
+    """The captured-and-replayed training step is the same arithmetic as the eager one."""
+    from unet.models import AttentionUNet
+    from unet.parallel import BatchShardedTrainer
+    from unet.utils.loss import DiceBCELoss
+    x, t = O.synthetic_batch(2, 64, 64, seed=9, fg_fraction=0.05)
+    x, t = x.cuda(), t.cuda()
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(3)
+        model = AttentionUNet(1, 2, True, 32).cuda()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=True, foreach=True)
+        tr = BatchShardedTrainer(model, DiceBCELoss(), opt, grad_clip=1.0, cuda_graph=use_graph, graph_warmup=2)
+        losses = [tr.step(x, t).item() for _ in range(6)]
+        results.append((losses, [p.detach().clone() for p in model.parameters()],
+                        int(model.inc.double_conv[1].num_batches_tracked)))
+    (l0, p0, n0), (l1, p1, n1) = results
+    assert n0 == n1 == 6
+    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert torch.equal(a, b)

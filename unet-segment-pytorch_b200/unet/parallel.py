@@ -42,14 +42,21 @@ class BatchShardedTrainer:
     """
 
     def __init__(self, model, criterion, optimizer, grad_clip: float = 0.0, bucket_mb: float = 24.0,
-                 process_group=None):
+                 process_group=None, cuda_graph: bool = False, graph_warmup: int = 3):
         self.model, self.criterion, self.optimizer, self.grad_clip = model, criterion, optimizer, grad_clip
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.buckets: List[_Bucket] = []
         self._build_buckets(bucket_mb)
-        self._loss_acc: Optional[torch.Tensor] = None
         self._steps = 0
+        # CUDA-graph replay of the whole step: a 512^2 batch-4 step is ~800 kernel launches, more
+        # host time than GPU time when issued one by one.  Every kernel of the path is
+        # stream-ordered with no host synchronisation, so the step is captured once per input
+        # shape (after `graph_warmup` eager steps) and replayed.
+        self.cuda_graph = cuda_graph
+        self.graph_warmup = graph_warmup
+        self._graphs = {}
+        self._eager_steps = {}
 
     # ------------------------------------------------------------------ flat gradient buckets
     def _build_buckets(self, bucket_mb: float) -> None:
@@ -84,13 +91,7 @@ class BatchShardedTrainer:
         return hook
 
     # ------------------------------------------------------------------ one optimizer step
-    def step(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
-        """One micro-batch per rank and one optimizer step.  ``images`` / ``masks`` may be host
-        (pinned) tensors: they are copied to this rank's GPU asynchronously.  Returns the
-        un-divided micro-batch loss as a 0-dim device tensor (no host sync)."""
-        dev = next(self.model.parameters()).device
-        images = images.to(dev, non_blocking=True)
-        masks = masks.to(dev, non_blocking=True)
+    def _step_body(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         self.model.train()
         for b in self.buckets:
             b.flat.zero_()
@@ -108,8 +109,49 @@ class BatchShardedTrainer:
         if self.grad_clip > 0:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip, foreach=True)
         self.optimizer.step()
-        self._steps += 1
         return loss.detach()
+
+    def _optimizer_capturable(self) -> bool:
+        return all(g.get("capturable", False) for g in self.optimizer.param_groups)
+
+    def step(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        """One micro-batch per rank and one optimizer step.  ``images`` / ``masks`` may be host
+        (pinned) tensors: they are copied to this rank's GPU asynchronously.  Returns the
+        un-divided micro-batch loss as a 0-dim device tensor (no host sync)."""
+        dev = next(self.model.parameters()).device
+        self._steps += 1
+        use_graph = self.cuda_graph and dev.type == "cuda" and self._optimizer_capturable()
+        if not use_graph:
+            return self._step_body(images.to(dev, non_blocking=True), masks.to(dev, non_blocking=True))
+        key = (tuple(images.shape), images.dtype, tuple(masks.shape), masks.dtype)
+        entry = self._graphs.get(key)
+        if entry is None:
+            done = self._eager_steps.get(key, 0)
+            if done < self.graph_warmup:
+                # eager warm-up (lazy initialisation, allocator, NCCL) on a side stream, as
+                # torch.cuda.graph requires
+                self._eager_steps[key] = done + 1
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    loss = self._step_body(images.to(dev, non_blocking=True), masks.to(dev, non_blocking=True))
+                torch.cuda.current_stream(dev).wait_stream(side)
+                return loss
+            gx = torch.empty(images.shape, dtype=images.dtype, device=dev)
+            gt = torch.empty(masks.shape, dtype=masks.dtype, device=dev)
+            gx.copy_(images, non_blocking=True)
+            gt.copy_(masks, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                gloss = self._step_body(gx, gt)
+            entry = self._graphs[key] = (graph, gx, gt, gloss)
+            # the capture itself does not execute: fall through and replay it for this step
+        graph, gx, gt, gloss = entry
+        gx.copy_(images, non_blocking=True)
+        gt.copy_(masks, non_blocking=True)
+        graph.replay()
+        return gloss
 
     @torch.no_grad()
     def evaluate(self, images: torch.Tensor, masks: torch.Tensor, metrics=None) -> torch.Tensor:
