@@ -130,6 +130,31 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def _shutdown(trainer, world):
+    """Leave a multi-rank run: drop the captured graphs (they pin the NCCL communicator), meet
+    the other ranks, tear the process group down — and never hang on the way out."""
+    sys.stdout.flush()
+    if world == 1:
+        return
+    import threading
+
+    import torch
+    import torch.distributed as dist
+
+    guard = threading.Timer(20.0, lambda: os._exit(0))
+    guard.daemon = True
+    guard.start()
+    try:
+        trainer.release_graphs()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001  the measurement is already printed
+        pass
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -147,6 +172,7 @@ def run_ours(args):
     from oracle import unet_oracle as O  # synthetic data generator only
     from unet import _C, kernels as K
     from unet.models import AttentionUNet
+    from unet.optim import FusedAdamW
     from unet.parallel import BatchShardedTrainer
     from unet.utils.loss import DiceBCELoss
 
@@ -154,7 +180,7 @@ def run_ours(args):
     torch.manual_seed(42)  # configs/lung_tumor.yaml:69
     model = AttentionUNet(n_channels=1, n_classes=2, bilinear=True, base_features=64).to(dev)
     criterion = DiceBCELoss()
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-4, foreach=True, capturable=True)
+    opt = FusedAdamW(model.parameters(), lr=5e-5, weight_decay=1e-4)   # train.py:346-350, fused with the clip
     trainer = BatchShardedTrainer(model, criterion, opt, grad_clip=1.0, cuda_graph=not args.no_graph)
 
     x_host, t_host = O.synthetic_batch(B, H, W, seed=1234 + rank)
@@ -213,8 +239,7 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _shutdown(trainer, world)
         return
 
     peaks, peak_src = load_peaks()
@@ -255,8 +280,7 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    _shutdown(trainer, world)
 
 
 def main():

@@ -64,9 +64,10 @@ int ub2_conv_wgrad(const void* in0, int ld_in0, int C0, const void* in1, int ld_
                    const void* dy, int ld_dy, float* partial, int max_splits, int* splits_used,
                    int N, int H, int W, int Cout, int taps, int splits_override, void* stream);
 
-/* grad (Cout,Cin,k,k fp32, the .grad of the nn.Conv2d weight) += sum over splits. */
-int ub2_wgrad_reduce(const float* partial, int splits, int Cout, int Cin, int taps, float* grad,
-                     void* stream);
+/* grad (Cout,Cin,k,k fp32, the .grad of the nn.Conv2d weight) = or += (accumulate) the sum over
+ * splits, in a fixed order.  `partial` is scratch: with many splits slot 0 is overwritten. */
+int ub2_wgrad_reduce(float* partial, int splits, int Cout, int Cin, int taps, float* grad,
+                     int accumulate, void* stream);
 
 /* OIHW fp32 parameter -> bf16 packs: fwd (Cout,taps,Cin) and dgrad (Cin,taps flipped,Cout);
  * either may be NULL; out_scale (optional, per Cout) folds a BatchNorm scale into the pack. */
@@ -190,6 +191,24 @@ int ub2_seg_stats_bwd(const float* logits, const long long* targets, const float
 int ub2_confusion(const void* pred, const long long* target, int mode, int N, int C, long long HW,
                   long long ignore_index, int has_ignore, float threshold, long long* cm,
                   unsigned char* mask_out, void* stream);
+
+/* ======================= optimizer tail ================================== */
+
+/* torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) (scripts/train.py:141) fused with
+ * torch.optim.AdamW.step() (optimizer built at scripts/train.py:346-350), multi-tensor.
+ * Device tables: ptrs (4,T) int64 = {param, grad, exp_avg, exp_avg_sq} fp32 pointers; numel (T)
+ * int64; group (T) int32 row of `hyper`; chunks (nchunks,2) int32 = {tensor, first element}, each
+ * covering ub2_adamw_chunk_elems() elements; hyper (G,8) fp32 = {lr, beta1, beta2, eps,
+ * weight_decay, max_norm (row 0 only; <= 0: no clipping), -, -}; step (1) fp32 device counter.
+ * ub2_grad_sumsq writes one fp64 partial per chunk and increments *step; ub2_adamw_step folds
+ * them in a fixed order (deterministic), stores the total norm, and updates in place; with
+ * write_grads the clipped gradients are written back like clip_grad_norm_ does. */
+int ub2_adamw_chunk_elems(void);
+int ub2_grad_sumsq(const long long* ptrs, const long long* numel, const int* chunks, int nchunks, int T,
+                   double* partial, float* step, void* stream);
+int ub2_adamw_step(const long long* ptrs, const long long* numel, const int* group, const int* chunks,
+                   int nchunks, int T, const double* partial, const float* hyper, const float* step,
+                   float* total_norm, int write_grads, void* stream);
 
 #ifdef __cplusplus
 }

@@ -138,3 +138,39 @@ def test_conv_wgrad(n, h, w, c0, c1, cout, taps):
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 2e-3 * scale + 1e-3, f"wgrad max err {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("cout,cin,taps,splits", [(64, 64, 9, 1), (64, 64, 9, 37), (32, 64, 1, 5), (48, 80, 9, 9),
+                                                   (256, 512, 9, 2), (16, 16, 1, 12)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_wgrad_reduce(cout, cin, taps, splits, accumulate):
+    """Split-K fold into the OIHW .grad: both the direct and the pre-summed (> 8 splits) path."""
+    from unet import kernels as K
+
+    k = 3 if taps == 9 else 1
+    g = torch.Generator().manual_seed(5)
+    part = torch.randn(splits, taps * cin, cout, generator=g)
+    base = torch.randn(cout, cin, k, k, generator=g)
+    ref = part.double().sum(0).reshape(k, k, cin, cout).permute(3, 2, 0, 1).float()
+    if accumulate:
+        ref = ref + base
+    grad = base.clone().cuda()
+    K.wgrad_reduce(part.cuda(), cout, cin, taps, grad, accumulate=accumulate)
+    assert torch.allclose(grad.cpu(), ref, rtol=1e-5, atol=1e-5 * splits ** 0.5)
+
+
+@pytest.mark.parametrize("cout,cin,k", [(64, 64, 3), (128, 64, 3), (32, 64, 1), (48, 80, 3), (512, 1024, 3), (16, 16, 1)])
+def test_pack_conv_weight(cout, cin, k):
+    """OIHW fp32 -> the two bf16 packs, bit-exact (round to nearest even), with and without a folded scale."""
+    from unet import kernels as K
+
+    g = torch.Generator().manual_seed(6)
+    w = torch.randn(cout, cin, k, k, generator=g)
+    sc = torch.rand(cout, generator=g) + 0.5
+    for scale in (None, sc):
+        ws = w if scale is None else w * scale.view(-1, 1, 1, 1)
+        fwd, dg = K.pack_conv_weight(w.cuda(), True, True, out_scale=None if scale is None else scale.cuda())
+        ref_f = ws.permute(0, 2, 3, 1).reshape(cout, k * k, cin).bfloat16()
+        ref_d = ws.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k, cout).bfloat16()
+        assert torch.equal(fwd.cpu(), ref_f)
+        assert torch.equal(dg.cpu(), ref_d)

@@ -1,0 +1,46 @@
+"""Bilinear (align_corners=True) up-sampling kernels against ATen's own forward and autograd
+(layers.py:78, :98-102, :183)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# n, hin, win, hu, wu, Ho, Wo, C
+CASES = [
+    (2, 32, 32, 64, 64, 64, 64, 64),      # exact 2x, tiled transpose
+    (1, 64, 128, 128, 256, 128, 256, 32),
+    (2, 37, 50, 74, 100, 75, 101, 16),    # F.pad to an odd skip size
+    (1, 8, 8, 16, 16, 16, 16, 48),        # tiny: staged region would not fit -> direct kernel
+    (2, 16, 16, 33, 33, 33, 33, 24),      # F.interpolate to an arbitrary size, C not a multiple of 16
+    (1, 20, 24, 47, 55, 47, 55, 64),      # gate-style resize (scale ~0.41)
+    (1, 1, 1, 2, 2, 2, 2, 16),
+]
+
+
+def _ref_up(x, hu, wu, ho, wo):
+    y = F.interpolate(x, size=(hu, wu), mode="bilinear", align_corners=True)
+    dy, dx = ho - hu, wo - wu
+    return F.pad(y, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+
+
+@pytest.mark.parametrize("n,hin,win,hu,wu,ho,wo,c", CASES)
+def test_upsample_fwd_bwd(n, hin, win, hu, wu, ho, wo, c):
+    from unet import kernels as K
+
+    g = torch.Generator().manual_seed(hin * 131 + c)
+    x = torch.randn(n, hin, win, c, generator=g).bfloat16()
+    dout = torch.randn(n, ho, wo, c, generator=g).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = _ref_up(xr, hu, wu, ho, wo)
+    ref.backward(dout.float().permute(0, 3, 1, 2))
+    got = K.upsample(x.cuda(), hu, wu, ho, wo).float().cpu()
+    assert torch.allclose(got, ref.detach().permute(0, 2, 3, 1), rtol=2 ** -7, atol=2 ** -7)
+    ref_g = xr.grad.permute(0, 2, 3, 1)
+    got_g = K.upsample_bwd(dout.cuda(), hin, win, hu, wu).float().cpu()
+    assert torch.allclose(got_g, ref_g, rtol=2 ** -7, atol=2 ** -6), (got_g - ref_g).abs().max()
+    # accumulate into an existing gradient
+    base = torch.randn(n, hin, win, c, generator=g).bfloat16()
+    acc = base.clone().cuda()
+    K.upsample_bwd(dout.cuda(), hin, win, hu, wu, into=acc)
+    assert torch.allclose(acc.float().cpu(), ref_g + base.float(), rtol=2 ** -6, atol=2 ** -5)

@@ -10,46 +10,130 @@
 
 namespace ub2 {
 
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
-                                   __nv_bfloat16* __restrict__ dgrad, int Cout, int Cin, int taps,
-                                   const float* __restrict__ out_scale) {
-  const long long total = static_cast<long long>(Cout) * Cin * taps;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    // i indexes OIHW: ((co*Cin + ci)*taps + t)
-    const int t = static_cast<int>(i % taps);
-    const int ci = static_cast<int>((i / taps) % Cin);
-    const int co = static_cast<int>(i / (static_cast<long long>(taps) * Cin));
-    float v = __ldg(w + i);
-    if (out_scale != nullptr) v *= __ldg(out_scale + co);  // BatchNorm folded into the weights (eval)
-    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-    if (fwd != nullptr) fwd[(static_cast<size_t>(co) * taps + t) * Cin + ci] = b;
-    if (dgrad != nullptr) dgrad[(static_cast<size_t>(ci) * taps + (taps - 1 - t)) * Cout + co] = b;
+// One block = a 16 (co) x 16 (ci) x TAPS tile, one or nine elements per thread with every load
+// issued before the first store.  The OIHW rows are read contiguously (16*TAPS floats per co),
+// rounded to bf16 into shared memory, and both packs are written in 32-byte runs along their own
+// fastest axis (ci for the forward pack, co for the data-gradient pack).
+static constexpr int kPackT = 16;
+
+template <int TAPS>
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
+                   __nv_bfloat16* __restrict__ dgrad, int Cout, int Cin,
+                   const float* __restrict__ out_scale) {
+  __shared__ __nv_bfloat16 tile[kPackT][kPackT * TAPS + 2];
+  const int ci0 = blockIdx.x * kPackT, co0 = blockIdx.y * kPackT;
+  const int nci = min(kPackT, Cin - ci0), nco = min(kPackT, Cout - co0);
+  const int row = nci * TAPS;  // contiguous floats per output channel in this tile
+  const int tid = threadIdx.x;
+  float v[TAPS];
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) {
+    const int idx = tid + k * 256;
+    const int col = idx / row, j = idx - col * row;
+    v[k] = 0.f;
+    if (col < nco) {
+      v[k] = __ldg(w + (static_cast<size_t>(co0 + col) * Cin + ci0) * TAPS + j);
+      if (out_scale != nullptr) v[k] *= __ldg(out_scale + co0 + col);  // BatchNorm folded (eval)
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) {
+    const int idx = tid + k * 256;
+    const int col = idx / row, j = idx - col * row;
+    if (col < nco) tile[col][j] = __float2bfloat16_rn(v[k]);
+  }
+  __syncthreads();
+  if (fwd != nullptr) {
+#pragma unroll
+    for (int k = 0; k < TAPS; ++k) {
+      const int idx = tid + k * 256;
+      const int cil = idx % nci;
+      const int t = (idx / nci) % TAPS;
+      const int col = idx / row;
+      if (col < nco)
+        fwd[(static_cast<size_t>(co0 + col) * TAPS + t) * Cin + ci0 + cil] = tile[col][cil * TAPS + t];
+    }
+  }
+  if (dgrad != nullptr) {
+#pragma unroll
+    for (int k = 0; k < TAPS; ++k) {
+      const int idx = tid + k * 256;
+      const int col = idx % nco;
+      const int t = (idx / nco) % TAPS;
+      const int cil = idx / (nco * TAPS);
+      if (cil < nci)
+        dgrad[(static_cast<size_t>(ci0 + cil) * TAPS + (TAPS - 1 - t)) * Cout + co0 + col] =
+            tile[col][cil * TAPS + t];
+    }
   }
 }
 
-// grad[co][ci][t] += sum_s partial[s][t*Cin + ci][co];  blockDim = (32, 8): x walks the partial
-// layout (coalesced), y strides over the splits; fixed summation order (deterministic).
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin,
-                                    int taps, float* __restrict__ grad) {
-  __shared__ float s_red[8][33];
-  const long long total = static_cast<long long>(Cout) * Cin * taps;
-  const long long i = static_cast<long long>(blockIdx.x) * 32 + threadIdx.x;
-  float a = 0.f;
-  if (i < total) {
-    for (int s = threadIdx.y; s < splits; s += 8) a += __ldg(partial + s * total + i);
+// Stage 1 of the split-K fold when there are many splits: partial[0][i] = sum_s partial[s][i],
+// float4 columns x 8 split lanes per block, fixed summation order (deterministic).  In place: every
+// element of slot 0 is read (by lane 0) before the block-wide barrier and written after it.
+__global__ void __launch_bounds__(256)
+wgrad_presum_kernel(float* __restrict__ partial, int splits, long long quads) {
+  __shared__ float4 s_red[8][32];
+  const long long q = static_cast<long long>(blockIdx.x) * 32 + threadIdx.x;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < quads) {
+    const float4* src = reinterpret_cast<const float4*>(partial) + q;
+#pragma unroll 4
+    for (int s = threadIdx.y; s < splits; s += 8) {
+      const float4 v = src[static_cast<size_t>(s) * quads];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
   }
   s_red[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
-  if (threadIdx.y == 0 && i < total) {
-    float t = 0.f;
+  if (threadIdx.y == 0 && q < quads) {
+    float4 t = s_red[0][threadIdx.x];
 #pragma unroll
-    for (int y = 0; y < 8; ++y) t += s_red[y][threadIdx.x];
-    const int co = static_cast<int>(i % Cout);
-    const long long m = i / Cout;
-    const int ci = static_cast<int>(m % Cin);
-    const int tp = static_cast<int>(m / Cin);
-    grad[(static_cast<size_t>(co) * Cin + ci) * taps + tp] += t;
+    for (int y = 1; y < 8; ++y) {
+      const float4 v = s_red[y][threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reinterpret_cast<float4*>(partial)[q] = t;
+  }
+}
+
+// grad[co][ci][t] (+)= sum_s partial[s][t*Cin + ci][co].  One block = 32 co x 8 ci x TAPS: the
+// partial rows are read along co (coalesced; a thread's TAPS rows are independent loads in
+// flight together), transposed through shared memory, and each output channel's 8*TAPS
+// consecutive OIHW floats are written together.  Fixed summation order (deterministic).
+static constexpr int kRedCi = 8;
+
+template <int TAPS>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin,
+                    float* __restrict__ grad, int accumulate) {
+  __shared__ float tile[32][kRedCi * TAPS + 1];
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * kRedCi;
+  const int nci = min(kRedCi, Cin - ci0);
+  const size_t total = static_cast<size_t>(Cout) * Cin * TAPS;
+  const int co = co0 + threadIdx.x;
+  const int cil = threadIdx.y;      // blockDim.y == kRedCi: one source channel per thread row
+  float a[TAPS];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) a[t] = 0.f;
+  if (co < Cout && cil < nci) {
+    const float* src = partial + static_cast<size_t>(ci0 + cil) * Cout + co;
+    for (int s = 0; s < splits; ++s) {
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) a[t] += __ldg(src + s * total + static_cast<size_t>(t) * Cin * Cout);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) tile[threadIdx.x][cil * TAPS + t] = a[t];
+  __syncthreads();
+  const int row = nci * TAPS;
+  for (int col = threadIdx.y; col < 32 && co0 + col < Cout; col += 8) {
+    float* dst = grad + (static_cast<size_t>(co0 + col) * Cin + ci0) * TAPS;
+    for (int j = threadIdx.x; j < row; j += 32) {
+      const float v = tile[col][j];
+      dst[j] = accumulate ? dst[j] + v : v;
+    }
   }
 }
 
@@ -64,18 +148,32 @@ int ub2_version(void) { return 100; }
 int ub2_pack_conv_weight(const float* w, void* fwd, void* dgrad, int Cout, int Cin, int taps,
                          const float* out_scale, void* stream) {
   if (Cout <= 0 || Cin <= 0 || (taps != 1 && taps != 9)) return UB2_ERR_SHAPE;
-  const long long total = static_cast<long long>(Cout) * Cin * taps;
-  pack_weight_kernel<<<stream_grid(total, 256, num_sms(), 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, static_cast<__nv_bfloat16*>(fwd), static_cast<__nv_bfloat16*>(dgrad), Cout, Cin, taps, out_scale);
+  const dim3 grid((Cin + kPackT - 1) / kPackT, (Cout + kPackT - 1) / kPackT);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (taps == 9)
+    pack_weight_kernel<9><<<grid, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(fwd),
+                                                static_cast<__nv_bfloat16*>(dgrad), Cout, Cin, out_scale);
+  else
+    pack_weight_kernel<1><<<grid, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(fwd),
+                                                static_cast<__nv_bfloat16*>(dgrad), Cout, Cin, out_scale);
   return static_cast<int>(cudaGetLastError());
 }
 
-int ub2_wgrad_reduce(const float* partial, int splits, int Cout, int Cin, int taps, float* grad,
-                     void* stream) {
-  if (Cout <= 0 || Cin <= 0 || splits <= 0) return UB2_ERR_SHAPE;
+int ub2_wgrad_reduce(float* partial, int splits, int Cout, int Cin, int taps, float* grad,
+                     int accumulate, void* stream) {
+  if (Cout <= 0 || Cin <= 0 || splits <= 0 || (taps != 1 && taps != 9)) return UB2_ERR_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long total = static_cast<long long>(Cout) * Cin * taps;
-  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), dim3(32, 8), 0,
-                        static_cast<cudaStream_t>(stream)>>>(partial, splits, Cout, Cin, taps, grad);
+  if (splits > 8 && total % 4 == 0) {  // many splits: column sums first, all SMs busy
+    const long long quads = total / 4;
+    wgrad_presum_kernel<<<static_cast<unsigned>((quads + 31) / 32), dim3(32, 8), 0, st>>>(partial, splits, quads);
+    splits = 1;
+  }
+  const dim3 grid((Cout + 31) / 32, (Cin + kRedCi - 1) / kRedCi);
+  if (taps == 9)
+    wgrad_reduce_kernel<9><<<grid, dim3(32, kRedCi), 0, st>>>(partial, splits, Cout, Cin, grad, accumulate);
+  else
+    wgrad_reduce_kernel<1><<<grid, dim3(32, kRedCi), 0, st>>>(partial, splits, Cout, Cin, grad, accumulate);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -110,10 +110,13 @@ def conv_wgrad(x0, dy, taps, x1=None, splits_override=0):
     return partial[: used.value]
 
 
-def wgrad_reduce(partial, cout, cin, taps, grad):
-    """grad (Cout,Cin,k,k) fp32 += sum over splits of partial (splits, taps*Cin, Cout)."""
+def wgrad_reduce(partial, cout, cin, taps, grad, accumulate=False):
+    """grad (Cout,Cin,k,k) fp32 = (or +=) sum over splits of partial (splits, taps*Cin, Cout).
+    ``partial`` is consumed (used as scratch)."""
     assert grad.dtype == F32 and grad.is_contiguous() and partial.is_contiguous()
-    _C.call("ub2_wgrad_reduce", ptr(partial), partial.shape[0], cout, cin, taps, ptr(grad), stream())
+    _C.call("ub2_wgrad_reduce", ptr(partial), partial.shape[0], cout, cin, taps, ptr(grad), int(accumulate),
+            stream())
+    return grad
 
 
 def pack_conv_weight(w, want_fwd=True, want_dgrad=True, out_scale=None):

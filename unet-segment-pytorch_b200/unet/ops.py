@@ -99,7 +99,7 @@ class ConvBnRelu(torch.autograd.Function):
         gw = None
         if ctx.needs_input_grad[2]:
             part = K.conv_wgrad(a0, dy, taps, x1=a1)
-            gw = torch.zeros(wshape, device=dy.device, dtype=torch.float32)
+            gw = torch.empty(wshape, device=dy.device, dtype=torch.float32)
             K.wgrad_reduce(part, cout, cin, taps, gw)
         d0 = d1 = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
@@ -217,9 +217,9 @@ class AttentionGateFn(torch.autograd.Function):
         grads, coef = K.gate_bwd_finalize(part2, count, gam_x, mx, ix, gam_g, mg, ig, frozen=not batch)
         dxp, dgup = K.gate_bwd_xg(ds, xp, q, coef)
         dq = K.upsample_bwd(dgup, hin, win, h, w)
-        gw_x = torch.zeros(sh_x, device=d.device, dtype=torch.float32)
+        gw_x = torch.empty(sh_x, device=d.device, dtype=torch.float32)
         K.wgrad_reduce(K.conv_wgrad(xn, dxp, 1), ci, cx, 1, gw_x)
-        gw_g = torch.zeros(sh_g, device=d.device, dtype=torch.float32)
+        gw_g = torch.empty(sh_g, device=d.device, dtype=torch.float32)
         K.wgrad_reduce(K.conv_wgrad(gn, dq, 1), ci, cg, 1, gw_g)
         K.conv_fwd(dxp, wxd, 1, out=dx, accumulate=True)
         dg = K.conv_fwd(dq, wgd, 1)
@@ -309,7 +309,7 @@ class ConvFn(torch.autograd.Function):
         d = to_nhwc(dy)
         gw = gb = None
         if ctx.needs_input_grad[1]:
-            gw = torch.zeros(ctx.meta, device=d.device, dtype=torch.float32)
+            gw = torch.empty(ctx.meta, device=d.device, dtype=torch.float32)
             K.wgrad_reduce(K.conv_wgrad(a, d, taps), cout, cin, taps, gw)
         if ctx.needs_input_grad[2]:
             gb = d.float().sum(dim=(0, 1, 2))

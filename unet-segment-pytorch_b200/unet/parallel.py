@@ -22,6 +22,8 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
+from .optim import FusedAdamW
+
 
 class _Bucket:
     __slots__ = ("flat", "params", "pending", "work")
@@ -71,12 +73,13 @@ class BatchShardedTrainer:
                 cur, cur_n = [], 0
         if cur:
             groups.append(cur)
+        pad = lambda n: (n + 31) & ~31   # every view starts on a 128-byte boundary (vector access)
         for g in groups:
-            flat = torch.zeros(sum(p.numel() for p in g), device=g[0].device, dtype=torch.float32)
+            flat = torch.zeros(sum(pad(p.numel()) for p in g), device=g[0].device, dtype=torch.float32)
             off = 0
             for p in g:
                 p.grad = flat[off:off + p.numel()].view_as(p)  # autograd accumulates in place into the view
-                off += p.numel()
+                off += pad(p.numel())
             b = _Bucket(flat, g)
             self.buckets.append(b)
             if self.world > 1:
@@ -106,12 +109,19 @@ class BatchShardedTrainer:
                     b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             for b in self.buckets:
                 b.work.wait()
-        if self.grad_clip > 0:
-            torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip, foreach=True)
-        self.optimizer.step()
+        if isinstance(self.optimizer, FusedAdamW):
+            # clip + AdamW in two multi-tensor launches (csrc/optim.cu)
+            self.optimizer.max_grad_norm = float(self.grad_clip)
+            self.optimizer.step()
+        else:
+            if self.grad_clip > 0:
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip, foreach=True)
+            self.optimizer.step()
         return loss.detach()
 
     def _optimizer_capturable(self) -> bool:
+        if isinstance(self.optimizer, FusedAdamW):
+            return True
         return all(g.get("capturable", False) for g in self.optimizer.param_groups)
 
     def step(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
@@ -150,8 +160,15 @@ class BatchShardedTrainer:
         graph, gx, gt, gloss = entry
         gx.copy_(images, non_blocking=True)
         gt.copy_(masks, non_blocking=True)
+        if isinstance(self.optimizer, FusedAdamW):
+            self.optimizer.sync_hyperparams()   # a scheduler may have changed the learning rate
         graph.replay()
         return gloss
+
+    def release_graphs(self) -> None:
+        """Drop the captured step graphs (they hold references to NCCL work and pool memory)."""
+        self._graphs.clear()
+        self._eager_steps.clear()
 
     @torch.no_grad()
     def evaluate(self, images: torch.Tensor, masks: torch.Tensor, metrics=None) -> torch.Tensor:
