@@ -285,3 +285,39 @@ def test_cuda_graph_step_equals_eager():
     assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
     for a, b in zip(p0, p1):
         assert torch.equal(a, b)
+
+
+def test_direct_gradient_sink_equals_autograd():
+    """With a gradient sink installed the kernels accumulate straight into param.grad and autograd
+    sees None: the result is bit-identical to the AccumulateGrad path, every parameter reported once."""
+    from unet import ops
+    from unet.models import AttentionUNet
+    from unet.utils.loss import DiceBCELoss
+    x, t = O.synthetic_batch(2, 64, 64, seed=11, fg_fraction=0.05)
+    x, t = x.cuda(), t.cuda()
+    torch.manual_seed(5)
+    model = AttentionUNet(1, 2, True, 32).cuda().train()
+    crit = DiceBCELoss()
+    crit(model(x), t).backward()
+    ref = [p.grad.clone() for p in model.parameters()]
+    for p in model.parameters():
+        p.grad = torch.zeros_like(p)
+    # BatchNorm buffers moved in the first pass; batch statistics do not depend on them
+    seen = []
+    ops.GRAD_SINK = seen.append
+    try:
+        crit(model(x), t).backward()
+    finally:
+        ops.GRAD_SINK = None
+    params = list(model.parameters())
+    assert sorted(id(p) for p in seen) == sorted(id(p) for p in params)
+    for p, r in zip(params, ref):
+        assert torch.equal(p.grad, r)
+    # accumulation semantics: a second backward adds
+    ops.GRAD_SINK = lambda p: None
+    try:
+        crit(model(x), t).backward()
+    finally:
+        ops.GRAD_SINK = None
+    for p, r in zip(params, ref):
+        assert torch.allclose(p.grad, 2 * r, rtol=1e-5, atol=1e-6)

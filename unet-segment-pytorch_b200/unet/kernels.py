@@ -164,9 +164,12 @@ def bn_act(y, scale, shift, relu=True, pool=False, write_act=True, want_idx=Fals
     return a, p
 
 
-def bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, relu=True, frozen=False):
+def bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, relu=True, frozen=False,
+                dgamma=None, dbeta=None):
     """BatchNorm(+ReLU, + max-pool routing) backward: returns (dy bf16, dgamma, dbeta).
-    ``frozen``: statistics were the running buffers (eval-mode backward), no mean terms."""
+    ``frozen``: statistics were the running buffers (eval-mode backward), no mean terms.
+    ``dgamma`` / ``dbeta``: existing fp32 gradient buffers to accumulate into (then None is
+    returned in their place)."""
     n, h, w, c, ld_y = _nhwc(y)
     ld_da = _nhwc(dA)[4] if dA is not None else 0
     ld_dp = _nhwc(dP)[4] if dP is not None else 0
@@ -175,21 +178,27 @@ def bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, relu=True, f
     partials = torch.empty((rows, 2, c), device=dev, dtype=F64)
     _C.call("ub2_bn_bwd_reduce", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(pidx), ptr(y), ld_y, ptr(scale),
             ptr(shift), ptr(partials), rows, n, h, w, c, int(relu), stream())
-    dgamma, dbeta, coef = bn_bwd_finalize(partials, n * h * w, gamma, mean, invstd, frozen)
+    dgamma, dbeta, coef = bn_bwd_finalize(partials, n * h * w, gamma, mean, invstd, frozen, dgamma, dbeta)
     dy = empty_nhwc(n, h, w, c, dev)
     _C.call("ub2_bn_bwd_apply", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(pidx), ptr(y), ld_y, ptr(scale),
             ptr(shift), ptr(coef), ptr(dy), c, n, h, w, c, int(relu), stream())
     return dy, dgamma, dbeta
 
 
-def bn_bwd_finalize(partials, count, gamma, mean, invstd, frozen=False):
-    """(sum g, sum g*y) rows -> (dgamma, dbeta, coef[3,C]) with dy = coef0*g + coef1*y + coef2."""
+def bn_bwd_finalize(partials, count, gamma, mean, invstd, frozen=False, dgamma=None, dbeta=None):
+    """(sum g, sum g*y) rows -> (dgamma, dbeta, coef[3,C]) with dy = coef0*g + coef1*y + coef2.
+    The kernel accumulates (+=): into fresh zeros, or into the given ``dgamma`` / ``dbeta``."""
     rows, _, c = partials.shape
-    grads = torch.zeros((2, c), device=partials.device, dtype=F32)
+    direct = dgamma is not None and dbeta is not None
+    if not direct:
+        grads = torch.zeros((2, c), device=partials.device, dtype=F32)
+        dgamma, dbeta = grads[0], grads[1]
     coef = torch.empty((3, c), device=partials.device, dtype=F32)
     _C.call("ub2_bn_bwd_finalize", ptr(partials), rows, c, c_double(float(count)), ptr(gamma), ptr(mean),
-            ptr(invstd), int(frozen), ptr(grads[0]), ptr(grads[1]), ptr(coef), stream())
-    return grads[0], grads[1], coef
+            ptr(invstd), int(frozen), ptr(dgamma), ptr(dbeta), ptr(coef), stream())
+    if direct:
+        return None, None, coef
+    return dgamma, dbeta, coef
 
 
 def maxpool_bwd(dP, pidx, a):
@@ -279,9 +288,12 @@ def gate_bwd_s(dpsin, psi, coef_psi, q, xp, sg, hg, sx, hx, wpsi):
     return ds, partials
 
 
-def gate_bwd_finalize(partials, count, gamma_x, mean_x, invstd_x, gamma_g, mean_g, invstd_g, frozen=False):
+def gate_bwd_finalize(partials, count, gamma_x, mean_x, invstd_x, gamma_g, mean_g, invstd_g, frozen=False,
+                      targets=None):
+    """``targets``: five existing fp32 buffers (dgamma_x, dbeta_x, dgamma_g, dbeta_g, dwpsi) to
+    accumulate into instead of fresh zeros."""
     rows, _, ci = partials.shape
-    grads = torch.zeros((5, ci), device=partials.device, dtype=F32)
+    grads = targets if targets is not None else torch.zeros((5, ci), device=partials.device, dtype=F32)
     coef = torch.empty((6, ci), device=partials.device, dtype=F32)
     _C.call("ub2_gate_bwd_finalize", ptr(partials), rows, ci, c_double(float(count)), ptr(gamma_x),
             ptr(mean_x), ptr(invstd_x), ptr(gamma_g), ptr(mean_g), ptr(invstd_g), int(frozen), ptr(grads[0]),
@@ -315,11 +327,13 @@ def conv_in_fwd(x, w, stats=True):
     return y, partials
 
 
-def conv_in_wgrad(x, dy, cout):
+def conv_in_wgrad(x, dy, cout, grad=None):
+    """``grad``: existing (Cout,Cin,3,3) fp32 buffer to accumulate into (default: fresh zeros)."""
     n, cin, h, wd = x.shape
     rows = _rows("ub2_conv_in_rows", n, h, wd, cout)
     partials = torch.empty((rows, cin, 9, cout), device=x.device, dtype=F64)
-    grad = torch.zeros((cout, cin, 3, 3), device=x.device, dtype=F32)
+    if grad is None:
+        grad = torch.zeros((cout, cin, 3, 3), device=x.device, dtype=F32)
     _C.call("ub2_conv_in_wgrad", ptr(x), ptr(dy), _nhwc(dy)[4], ptr(partials), rows, ptr(grad), n, cin,
             h, wd, cout, stream())
     return grad
@@ -333,15 +347,18 @@ def outc_fwd(a, w, bias):
     return logits
 
 
-def outc_bwd(dlogits, a, w, need_da=True):
+def outc_bwd(dlogits, a, w, need_da=True, dw=None, db=None):
+    """``dw`` / ``db``: existing fp32 gradient buffers to accumulate into (default: fresh zeros)."""
     n, h, wd, c, ld = _nhwc(a)
     k = w.shape[0]
     assert dlogits.dtype == F32 and dlogits.is_contiguous()
     rows = _rows("ub2_outc_rows", n, h, wd, c)
     partials = torch.empty((rows, k * c + k), device=a.device, dtype=F64)
     da = empty_nhwc(n, h, wd, c, a.device) if need_da else None
-    dw = torch.zeros((k, c, 1, 1), device=a.device, dtype=F32)
-    db = torch.zeros((k,), device=a.device, dtype=F32)
+    if dw is None:
+        dw = torch.zeros((k, c, 1, 1), device=a.device, dtype=F32)
+    if db is None:
+        db = torch.zeros((k,), device=a.device, dtype=F32)
     _C.call("ub2_outc_bwd", ptr(dlogits), ptr(a), ld, ptr(w), ptr(da), c, ptr(partials), rows, ptr(dw),
             ptr(db), n, h, wd, c, k, stream())
     return da, dw, db

@@ -15,6 +15,35 @@ from . import kernels as K
 BF16 = torch.bfloat16
 
 
+# ---------------------------------------------------------------------------------------------
+# Direct gradient accumulation.  When a sink is installed (BatchShardedTrainer does it for the
+# duration of its step), a backward pass accumulates each parameter gradient straight into the
+# existing ``param.grad`` buffer from inside the producing kernel and returns ``None`` for it, so
+# autograd launches no per-parameter ``grad += g`` kernel (92 of them per step) and no zero fill for
+# temporaries.  ``sink(param)`` is called once the gradient has been enqueued — the replacement
+# for a post-accumulate-grad hook.  Without a sink gradients flow through autograd as usual.
+GRAD_SINK = None
+
+
+def _grad_targets(*params):
+    """The .grad buffers of ``params`` if every one can be accumulated into in place, else None."""
+    if GRAD_SINK is None:
+        return None
+    out = []
+    for p in params:
+        g = getattr(p, "grad", None)
+        if (g is None or not p.is_leaf or g.dtype != torch.float32 or not g.is_contiguous()
+                or g.numel() != p.numel() or g.device != p.device):
+            return None
+        out.append(g)
+    return out
+
+
+def _grads_done(*params):
+    for p in params:
+        GRAD_SINK(p)
+
+
 def to_nhwc(x: torch.Tensor) -> torch.Tensor:
     """Logical NCHW tensor -> dense NHWC bf16 view (no copy if already channels_last bf16)."""
     if not x.is_cuda:
@@ -85,6 +114,7 @@ class ConvBnRelu(torch.autograd.Function):
             a, p = K.bn_act(y, scale, shift, relu=True, pool=False)
         ctx.save_for_backward(a0, a1, y, scale, shift, mean, invstd, gamma, wd, pidx)
         ctx.meta = (weight.shape, batch)
+        ctx.params = (weight, gamma, beta)
         return from_nhwc(a), (from_nhwc(p) if pool else None)
 
     @staticmethod
@@ -95,12 +125,22 @@ class ConvBnRelu(torch.autograd.Function):
         taps = kh * kw
         dA_n = to_nhwc(dA) if dA is not None else None
         dP_n = to_nhwc(dP) if dP is not None else None
-        dy, dgamma, dbeta = _bn_backward(dA_n, dP_n, pidx, y, scale, shift, mean, invstd, gamma, batch)
+        p_w, p_gamma, p_beta = ctx.params
+        bn_t = _grad_targets(p_gamma, p_beta) if ctx.needs_input_grad[3] and ctx.needs_input_grad[4] else None
+        dy, dgamma, dbeta = _bn_backward(dA_n, dP_n, pidx, y, scale, shift, mean, invstd, gamma, batch,
+                                         targets=bn_t)
+        if bn_t is not None:
+            _grads_done(p_gamma, p_beta)
         gw = None
         if ctx.needs_input_grad[2]:
             part = K.conv_wgrad(a0, dy, taps, x1=a1)
-            gw = torch.empty(wshape, device=dy.device, dtype=torch.float32)
-            K.wgrad_reduce(part, cout, cin, taps, gw)
+            w_t = _grad_targets(p_w)
+            if w_t is not None:
+                K.wgrad_reduce(part, cout, cin, taps, w_t[0], accumulate=True)
+                _grads_done(p_w)
+            else:
+                gw = torch.empty(wshape, device=dy.device, dtype=torch.float32)
+                K.wgrad_reduce(part, cout, cin, taps, gw)
         d0 = d1 = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             n, h, w, _ = a0.shape
@@ -113,8 +153,10 @@ class ConvBnRelu(torch.autograd.Function):
         return d0, d1, gw, dgamma, dbeta, None, None
 
 
-def _bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, batch, relu=True):
-    return K.bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, relu=relu, frozen=not batch)
+def _bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, batch, relu=True, targets=None):
+    dg, db = targets if targets is not None else (None, None)
+    return K.bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, relu=relu, frozen=not batch,
+                         dgamma=dg, dbeta=db)
 
 
 class ConvInBnRelu(torch.autograd.Function):
@@ -138,14 +180,27 @@ class ConvInBnRelu(torch.autograd.Function):
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(x, y, scale, shift, mean, invstd, gamma)
             ctx.meta = (weight.shape, batch)
+            ctx.params = (weight, gamma, beta)
         return from_nhwc(a)
 
     @staticmethod
     def backward(ctx, dA):
         x, y, scale, shift, mean, invstd, gamma = ctx.saved_tensors
         wshape, batch = ctx.meta
-        dy, dgamma, dbeta = _bn_backward(to_nhwc(dA), None, None, y, scale, shift, mean, invstd, gamma, batch)
-        gw = K.conv_in_wgrad(x, dy, wshape[0])
+        p_w, p_gamma, p_beta = ctx.params
+        bn_t = _grad_targets(p_gamma, p_beta) if ctx.needs_input_grad[2] and ctx.needs_input_grad[3] else None
+        dy, dgamma, dbeta = _bn_backward(to_nhwc(dA), None, None, y, scale, shift, mean, invstd, gamma, batch,
+                                         targets=bn_t)
+        if bn_t is not None:
+            _grads_done(p_gamma, p_beta)
+        gw = None
+        if ctx.needs_input_grad[1]:
+            w_t = _grad_targets(p_w)
+            if w_t is not None:
+                K.conv_in_wgrad(x, dy, wshape[0], grad=w_t[0])
+                _grads_done(p_w)
+            else:
+                gw = K.conv_in_wgrad(x, dy, wshape[0])
         return None, gw, dgamma, dbeta, None
 
 
@@ -199,6 +254,7 @@ class AttentionGateFn(torch.autograd.Function):
             ctx.save_for_backward(gn, xn, q, xp, psi, a, sg, hg, mg, ig, sx, hx, mx, ix, mp, ip, wgd, wxd,
                                   wpsi, gam_g, gam_x, gam_p)
             ctx.meta = (w_g.shape, w_x.shape, w_psi.shape, batch)
+            ctx.params = (w_g, w_x, w_psi, gam_g, bet_g, gam_x, bet_x, gam_p, bet_p)
         return from_nhwc(out)
 
     @staticmethod
@@ -211,18 +267,32 @@ class AttentionGateFn(torch.autograd.Function):
         ci = q.shape[3]
         count = n * h * w
         d = to_nhwc(dout)
+        p_wg, p_wx, p_wpsi, p_gg, p_bg, p_gx, p_bx, p_gp, p_bp = ctx.params
+        direct = _grad_targets(*ctx.params) if all(ctx.needs_input_grad[2:11]) else None
         dx, dpsin, part = K.gate_bwd_a(d, xn, a, psi)
-        dgam_p, dbet_p, coef_p = K.bn_bwd_finalize(part, count, gam_p, mp, ip, frozen=not batch)
+        if direct is not None:
+            t_wg, t_wx, t_wpsi, t_gg, t_bg, t_gx, t_bx, t_gp, t_bp = direct
+            _, _, coef_p = K.bn_bwd_finalize(part, count, gam_p, mp, ip, frozen=not batch, dgamma=t_gp, dbeta=t_bp)
+        else:
+            dgam_p, dbet_p, coef_p = K.bn_bwd_finalize(part, count, gam_p, mp, ip, frozen=not batch)
         ds, part2 = K.gate_bwd_s(dpsin, psi, coef_p, q, xp, sg, hg, sx, hx, wpsi)
-        grads, coef = K.gate_bwd_finalize(part2, count, gam_x, mx, ix, gam_g, mg, ig, frozen=not batch)
+        grads, coef = K.gate_bwd_finalize(part2, count, gam_x, mx, ix, gam_g, mg, ig, frozen=not batch,
+                                          targets=[t_gx, t_bx, t_gg, t_bg, t_wpsi] if direct is not None else None)
         dxp, dgup = K.gate_bwd_xg(ds, xp, q, coef)
         dq = K.upsample_bwd(dgup, hin, win, h, w)
-        gw_x = torch.empty(sh_x, device=d.device, dtype=torch.float32)
-        K.wgrad_reduce(K.conv_wgrad(xn, dxp, 1), ci, cx, 1, gw_x)
-        gw_g = torch.empty(sh_g, device=d.device, dtype=torch.float32)
-        K.wgrad_reduce(K.conv_wgrad(gn, dq, 1), ci, cg, 1, gw_g)
+        if direct is not None:
+            K.wgrad_reduce(K.conv_wgrad(xn, dxp, 1), ci, cx, 1, t_wx, accumulate=True)
+            K.wgrad_reduce(K.conv_wgrad(gn, dq, 1), ci, cg, 1, t_wg, accumulate=True)
+        else:
+            gw_x = torch.empty(sh_x, device=d.device, dtype=torch.float32)
+            K.wgrad_reduce(K.conv_wgrad(xn, dxp, 1), ci, cx, 1, gw_x)
+            gw_g = torch.empty(sh_g, device=d.device, dtype=torch.float32)
+            K.wgrad_reduce(K.conv_wgrad(gn, dq, 1), ci, cg, 1, gw_g)
         K.conv_fwd(dxp, wxd, 1, out=dx, accumulate=True)
         dg = K.conv_fwd(dq, wgd, 1)
+        if direct is not None:
+            _grads_done(*ctx.params)
+            return (from_nhwc(dg), from_nhwc(dx)) + (None,) * 12
         return (from_nhwc(dg), from_nhwc(dx), gw_g, gw_x, grads[4].reshape(sh_p), grads[2], grads[3],
                 grads[0], grads[1], dgam_p, dbet_p, None, None, None)
 
@@ -235,14 +305,22 @@ class OutConvFn(torch.autograd.Function):
         a = to_nhwc(x)
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(a, weight)
+            ctx.params = (weight, bias)
         return K.outc_fwd(a, weight.reshape(weight.shape[0], -1), bias)
 
     @staticmethod
     def backward(ctx, dlogits):
         a, weight = ctx.saved_tensors
+        direct = _grad_targets(*ctx.params) if ctx.needs_input_grad[1] and ctx.needs_input_grad[2] else None
         da, dw, db = K.outc_bwd(dlogits.contiguous().float(), a, weight.reshape(weight.shape[0], -1),
-                                need_da=ctx.needs_input_grad[0])
-        return (from_nhwc(da) if da is not None else None), dw.reshape(weight.shape), db
+                                need_da=ctx.needs_input_grad[0],
+                                dw=direct[0] if direct is not None else None,
+                                db=direct[1] if direct is not None else None)
+        da = from_nhwc(da) if da is not None else None
+        if direct is not None:
+            _grads_done(*ctx.params)
+            return da, None, None
+        return da, dw.reshape(weight.shape), db
 
 
 class SegStats(torch.autograd.Function):

@@ -22,6 +22,7 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
+from . import ops
 from .optim import FusedAdamW
 
 
@@ -49,6 +50,7 @@ class BatchShardedTrainer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.buckets: List[_Bucket] = []
+        self._bucket_of = {}
         self._build_buckets(bucket_mb)
         self._steps = 0
         # CUDA-graph replay of the whole step: a 512^2 batch-4 step is ~800 kernel launches, more
@@ -82,16 +84,25 @@ class BatchShardedTrainer:
                 off += pad(p.numel())
             b = _Bucket(flat, g)
             self.buckets.append(b)
-            if self.world > 1:
-                for p in g:
+            for p in g:
+                self._bucket_of[id(p)] = b
+                if self.world > 1:
                     p.register_post_accumulate_grad_hook(self._make_hook(b))
 
+    def _bucket_ready(self, bucket: _Bucket) -> None:
+        bucket.pending -= 1
+        if bucket.pending == 0 and self.world > 1:
+            bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def _make_hook(self, bucket: _Bucket):
-        def hook(_param):
-            bucket.pending -= 1
-            if bucket.pending == 0:
-                bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        return hook
+        return lambda _param: self._bucket_ready(bucket)
+
+    def _grad_sink(self, param) -> None:
+        """Called by unet.ops when a kernel has accumulated ``param``'s gradient straight into its
+        bucket view (no autograd AccumulateGrad node runs for it, hence no hook)."""
+        b = self._bucket_of.get(id(param))
+        if b is not None:
+            self._bucket_ready(b)
 
     # ------------------------------------------------------------------ one optimizer step
     def _step_body(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
@@ -102,7 +113,11 @@ class BatchShardedTrainer:
             b.work = None
         outputs = self.model(images)
         loss = self.criterion(outputs, masks)
-        (loss / self.world).backward()
+        prev_sink, ops.GRAD_SINK = ops.GRAD_SINK, self._grad_sink
+        try:
+            (loss / self.world).backward()
+        finally:
+            ops.GRAD_SINK = prev_sink
         if self.world > 1:
             for b in self.buckets:
                 if b.work is None:  # a parameter without gradient this step
