@@ -40,6 +40,7 @@ struct ConvFwdParams {
   __nv_bfloat16* out0;
   __nv_bfloat16* out1;
   int ld0, ld1, split, accumulate, relu;
+  int wide_store;  // 256-bit epilogue stores: pointers 32-byte aligned, ld / split multiples of 16
   const float* scale;
   const float* shift;
   double* stats;
@@ -83,5 +84,11 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C,
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
                  uint32_t bc, uint32_t br, int swizzle_bytes);
 int num_sms();
+
+inline int conv_wide_store_ok(const void* out0, int ld0, const void* out1, int ld1, int split, int Cout) {
+  if ((reinterpret_cast<uintptr_t>(out0) & 31) != 0 || ld0 % 16 != 0 || Cout % 16 != 0) return 0;
+  if (out1 != nullptr && ((reinterpret_cast<uintptr_t>(out1) & 31) != 0 || ld1 % 16 != 0 || split % 16 != 0)) return 0;
+  return 1;
+}
 
 }  // namespace ub2

@@ -75,6 +75,7 @@ __device__ __forceinline__ void epi_chunk(const ConvFwdParams& p, uint32_t taddr
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
+  uint4 held = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     uint4 o;
@@ -82,7 +83,20 @@ __device__ __forceinline__ void epi_chunk(const ConvFwdParams& p, uint32_t taddr
     o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
     o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
     o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-    if (dvalid[g]) *reinterpret_cast<uint4*>(dst[g]) = o;
+    // 16-channel pairs go out as one 256-bit store: a warp's rows are 128+ bytes apart, so a
+    // 16-byte store per lane fills half a 32-byte sector and every sector is written twice
+    if (p.wide_store) {
+      if ((g & 1) == 0) {
+        held = o;
+      } else if (dvalid[g - 1] && dvalid[g] && dst[g] == dst[g - 1] + 8) {
+        st_global_256(dst[g - 1], held, o);
+      } else {
+        if (dvalid[g - 1]) *reinterpret_cast<uint4*>(dst[g - 1]) = held;
+        if (dvalid[g]) *reinterpret_cast<uint4*>(dst[g]) = o;
+      }
+    } else if (dvalid[g]) {
+      *reinterpret_cast<uint4*>(dst[g]) = o;
+    }
     if (want_stats) {
       // statistics of the values as stored (bf16-rounded): BatchNorm then normalises
       // exactly the tensor it measured; masked pixels / channels count as 0

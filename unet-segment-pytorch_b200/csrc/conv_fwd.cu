@@ -16,6 +16,7 @@
 // inference), optional accumulate into the destination, bf16 store, and
 // per-channel sum / sum-of-squares of the rounded outputs (BatchNorm batch
 // statistics, layers.py:33) reduced with a register butterfly.
+#include <cstdlib>
 #include "conv.h"
 #include "conv_epilogue.cuh"
 #include "ptx.cuh"
@@ -274,6 +275,10 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   p.accumulate = a.accumulate;
   p.scale = a.scale; p.shift = a.shift; p.relu = a.relu;
   p.stats = a.stats;
+  {
+    static const int wide_env = [] { const char* e = getenv("UB2_WIDE_STORE"); return e ? atoi(e) : 1; }();
+    p.wide_store = wide_env && conv_wide_store_ok(a.out0, a.ld0, a.out1, a.ld1, a.split, a.Cout);
+  }
 
   CUtensorMap tmA0, tmA1, tmB;
   const uint32_t boxA[4] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(p.BW),

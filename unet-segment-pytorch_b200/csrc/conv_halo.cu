@@ -11,6 +11,7 @@
 // the R accumulators, which all live in TMEM (2 x R x N columns, double buffered across items).
 //
 // Warp roles, barriers and epilogue are those of conv_fwd.cu.
+#include <cstdlib>
 #include "conv.h"
 #include "conv_epilogue.cuh"
 #include "ptx.cuh"
@@ -251,7 +252,9 @@ int conv_halo_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   p.b_stage_bytes = BN * 128;  // BN % 16 == 0 and kc == 64: a multiple of 1024 only if BN % 8 == 0
   p.b_stage_bytes = (p.b_stage_bytes + 1023) & ~1023;
   int R = 256 / bn_cols;  // two accumulator sets of R tiles in 512 TMEM columns
-  if (R > 4) R = 4;
+  if (R > 3) R = 3;       // R = 4 leaves room for only 3 weight stages: the B ring starves (measured)
+  static const int r_env = [] { const char* e = getenv("UB2_HALO_R"); return e ? atoi(e) : 0; }();
+  if (r_env > 0 && r_env < R) R = r_env;   // tuning experiments
   if (R > a.H) R = a.H;
   int b_stages = 0;
   for (; R >= 1; --R) {
@@ -274,6 +277,10 @@ int conv_halo_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   p.accumulate = a.accumulate;
   p.scale = a.scale; p.shift = a.shift; p.relu = a.relu;
   p.stats = a.stats;
+  {
+    static const int wide_env = [] { const char* e = getenv("UB2_WIDE_STORE"); return e ? atoi(e) : 1; }();
+    p.wide_store = wide_env && conv_wide_store_ok(a.out0, a.ld0, a.out1, a.ld1, a.split, a.Cout);
+  }
 
   CUtensorMap tmA0, tmA1, tmB;
   const uint32_t boxA[4] = {64u, static_cast<uint32_t>(kRW), static_cast<uint32_t>(R + 2), 1u};

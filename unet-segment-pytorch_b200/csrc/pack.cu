@@ -16,14 +16,16 @@ namespace ub2 {
 // fastest axis (ci for the forward pack, co for the data-gradient pack).
 static constexpr int kPackT = 16;
 
-template <int TAPS>
+// FULL: Cin and Cout are multiples of 16, so every index split below divides by a constant (with
+// run-time tile extents the integer divisions make the kernel instruction bound).
+template <int TAPS, bool FULL>
 __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
                    __nv_bfloat16* __restrict__ dgrad, int Cout, int Cin,
                    const float* __restrict__ out_scale) {
   __shared__ __nv_bfloat16 tile[kPackT][kPackT * TAPS + 2];
   const int ci0 = blockIdx.x * kPackT, co0 = blockIdx.y * kPackT;
-  const int nci = min(kPackT, Cin - ci0), nco = min(kPackT, Cout - co0);
+  const int nci = FULL ? kPackT : min(kPackT, Cin - ci0), nco = FULL ? kPackT : min(kPackT, Cout - co0);
   const int row = nci * TAPS;  // contiguous floats per output channel in this tile
   const int tid = threadIdx.x;
   float v[TAPS];
@@ -150,12 +152,13 @@ int ub2_pack_conv_weight(const float* w, void* fwd, void* dgrad, int Cout, int C
   if (Cout <= 0 || Cin <= 0 || (taps != 1 && taps != 9)) return UB2_ERR_SHAPE;
   const dim3 grid((Cin + kPackT - 1) / kPackT, (Cout + kPackT - 1) / kPackT);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (taps == 9)
-    pack_weight_kernel<9><<<grid, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(fwd),
-                                                static_cast<__nv_bfloat16*>(dgrad), Cout, Cin, out_scale);
-  else
-    pack_weight_kernel<1><<<grid, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(fwd),
-                                                static_cast<__nv_bfloat16*>(dgrad), Cout, Cin, out_scale);
+  __nv_bfloat16* f = static_cast<__nv_bfloat16*>(fwd);
+  __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dgrad);
+  const bool full = Cin % kPackT == 0 && Cout % kPackT == 0;
+  if (taps == 9 && full) pack_weight_kernel<9, true><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
+  else if (taps == 9) pack_weight_kernel<9, false><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
+  else if (full) pack_weight_kernel<1, true><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
+  else pack_weight_kernel<1, false><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -178,51 +178,56 @@ upsample_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ dout, int ld_dout,
   constexpr int kLoads = (kBT_RH * kBT_RW * 2 + 255) / 256;
   uint4 stage[kLoads];
 #pragma unroll
-  for (int k = 0; k < kLoads; ++k) {
+  for (int k = 0; k < kLoads; ++k) {   // the staged region has a fixed pitch: constant divisors
     const int idx = tid + k * 256;
-    const int col = (idx >> 1) % RW;
-    const int row = (idx >> 1) / RW;
+    const int col = (idx >> 1) % kBT_RW;
+    const int row = (idx >> 1) / kBT_RW;
     const int ho = ulo + row + g.pt, wo = vlo + col + g.pl;
     stage[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (row < RH && ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo)
+    if (row < RH && col < RW && ho >= 0 && ho < g.Ho && wo >= 0 && wo < g.Wo)
       stage[k] = __ldg(reinterpret_cast<const uint4*>(src + (static_cast<size_t>(ho) * g.Wo + wo) * ld_dout) + (idx & 1));
   }
 #pragma unroll
   for (int k = 0; k < kLoads; ++k) {
     const int idx = tid + k * 256;
-    if (idx < RH * RW * 2) region[idx] = stage[k];
+    if (idx < kBT_RH * kBT_RW * 2) region[idx] = stage[k];
   }
   __syncthreads();
   const int half = tid & 1;
   const int wi = w0 + ((tid >> 1) & (kBT_W - 1));
   const int hi = h0 + (tid >> 5);
   if (wi >= g.win || hi >= g.hin) return;
-  int a_lo, a_hi;
-  dst_range(g.rh, hi, g.hu, a_lo, a_hi);
-  // column taps: candidates floor((wi-1)/r) .. +7 cover ceil((wi+1)/r) when r >= 0.4 (host check)
-  int b_lo = static_cast<int>(floorf((static_cast<float>(wi) - 1.f) / g.rw));
-  if (b_lo < 0) b_lo = 0;
-  float wv[kMaxTaps];
+  // Transposed bilinear weights are the hat function max(0, 1 - |r*u - i|) of the same fp32
+  // product ATen forms; with r >= 0.4 (host check) at most five destination rows / columns touch
+  // one source row / column, starting at the first u with r*u > i - 1.
+  const float fi = static_cast<float>(hi), fj = static_cast<float>(wi);
+  int u0 = static_cast<int>(floorf((fi - 1.f) / g.rh)) + 1;
+  int v0 = static_cast<int>(floorf((fj - 1.f) / g.rw)) + 1;
+  if (u0 < 0) u0 = 0;
+  if (v0 < 0) v0 = 0;
+  float wv[5];
+  int cv[5];
 #pragma unroll
-  for (int k = 0; k < kMaxTaps; ++k) {
-    const int v = b_lo + k;
-    wv[k] = (v < g.wu) ? tap_weight(g.rw, v, g.win, wi) : 0.f;
+  for (int k = 0; k < 5; ++k) {
+    const int v = v0 + k;
+    wv[k] = (v < g.wu) ? fmaxf(0.f, 1.f - fabsf(g.rw * static_cast<float>(v) - fj)) : 0.f;
+    cv[k] = (min(v, vhi) - vlo) * 2;   // clamped: a zero weight never multiplies stale shared memory
   }
   F8 acc;
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc.v[k] = 0.f;
-  for (int u = a_lo; u <= a_hi; ++u) {
-    const float wh = tap_weight(g.rh, u, g.hin, hi);
-    if (wh == 0.f) continue;
-    const uint4* rowp = region + ((u - ulo) * RW + (b_lo - vlo)) * 2 + half;
 #pragma unroll
-    for (int k = 0; k < kMaxTaps; ++k) {
-      if (wv[k] != 0.f) {
-        const F8 d = unpack8(rowp[k * 2]);
-        const float wt = wh * wv[k];
+  for (int kr = 0; kr < 5; ++kr) {
+    const int u = u0 + kr;
+    const float wh = (u < g.hu) ? fmaxf(0.f, 1.f - fabsf(g.rh * static_cast<float>(u) - fi)) : 0.f;
+    if (wh == 0.f) continue;   // warp-uniform: a warp is one source row of the tile
+    const uint4* rowp = region + (min(u, uhi) - ulo) * (kBT_RW * 2) + half;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc.v[c] = fmaf(wt, d.v[c], acc.v[c]);
-      }
+    for (int k = 0; k < 5; ++k) {
+      const F8 d = unpack8(rowp[cv[k]]);
+      const float wt = wh * wv[k];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc.v[c] = fmaf(wt, d.v[c], acc.v[c]);
     }
   }
   __nv_bfloat16* dst = din + ((static_cast<size_t>(n) * g.hin + hi) * g.win + wi) * ld_din + slab * 16 + half * 8;
@@ -240,7 +245,7 @@ static bool bwd_tiled_ok(const UpGeom& g) {
   const float span_h = (static_cast<float>(kBT_H) + 1.f) / g.rh + 5.f;
   const float span_w = (static_cast<float>(kBT_W) + 1.f) / g.rw + 5.f;
   // and every source column at most kMaxTaps candidate taps (2/r + 3 <= 8)
-  return span_h <= kBT_RH && span_w <= kBT_RW && g.rw >= 0.4f;
+  return span_h <= kBT_RH && span_w <= kBT_RW && g.rw >= 0.4f && g.rh >= 0.4f;
 }
 
 static dim3 up_block(int cgs) {
