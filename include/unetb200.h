@@ -73,6 +73,10 @@ int ub2_wgrad_reduce(float* partial, int splits, int Cout, int Cin, int taps, fl
  * either may be NULL; out_scale (optional, per Cout) folds a BatchNorm scale into the pack. */
 int ub2_pack_conv_weight(const float* w, void* fwd, void* dgrad, int Cout, int Cin, int taps,
                          const float* out_scale, void* stream);
+/* The same for many weights in one launch (once per optimizer step): desc (T,6) int64 =
+ * {w, fwd, dgrad, Cout, Cin, taps} with Cout and Cin multiples of 16; blocks (nblocks,4) int32 =
+ * {tensor, Cin tile, Cout tile, 0}, one per 16x16 channel tile. */
+int ub2_pack_conv_weights_multi(const long long* desc, const int* blocks, int nblocks, void* stream);
 
 /* ======================= BatchNorm / ReLU / MaxPool passes ============================== */
 

@@ -174,3 +174,20 @@ def test_pack_conv_weight(cout, cin, k):
         ref_d = ws.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k, cout).bfloat16()
         assert torch.equal(fwd.cpu(), ref_f)
         assert torch.equal(dg.cpu(), ref_d)
+
+
+def test_weight_packer_multi():
+    """One launch packs every registered weight exactly like the per-tensor kernel."""
+    from unet import kernels as K
+
+    g = torch.Generator().manual_seed(8)
+    ws = [torch.randn(s, generator=g).cuda() for s in [(64, 64, 3, 3), (128, 64, 3, 3), (32, 64, 1, 1),
+                                                        (256, 512, 3, 3), (64, 1, 3, 3), (1, 32, 1, 1)]]
+    packer = K.WeightPacker(ws)
+    packer.run()
+    assert packer.get(ws[4]) is None and packer.get(ws[5]) is None   # stem / psi: not tensor-core packs
+    for w in ws[:4]:
+        fwd, dg = packer.get(w)
+        rf, rd = K.pack_conv_weight(w, True, True)
+        assert torch.equal(fwd, rf) and torch.equal(dg, rd)
+    assert packer.get(ws[0].clone()) is None

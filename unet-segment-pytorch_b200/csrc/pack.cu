@@ -19,12 +19,11 @@ static constexpr int kPackT = 16;
 // FULL: Cin and Cout are multiples of 16, so every index split below divides by a constant (with
 // run-time tile extents the integer divisions make the kernel instruction bound).
 template <int TAPS, bool FULL>
-__global__ void __launch_bounds__(256)
-pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
-                   __nv_bfloat16* __restrict__ dgrad, int Cout, int Cin,
-                   const float* __restrict__ out_scale) {
-  __shared__ __nv_bfloat16 tile[kPackT][kPackT * TAPS + 2];
-  const int ci0 = blockIdx.x * kPackT, co0 = blockIdx.y * kPackT;
+__device__ __forceinline__ void pack_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
+                                          __nv_bfloat16* __restrict__ dgrad, int Cout, int Cin,
+                                          const float* __restrict__ out_scale, int ci_tile, int co_tile,
+                                          __nv_bfloat16 (*tile)[kPackT * 9 + 2]) {
+  const int ci0 = ci_tile * kPackT, co0 = co_tile * kPackT;
   const int nci = FULL ? kPackT : min(kPackT, Cin - ci0), nco = FULL ? kPackT : min(kPackT, Cout - co0);
   const int row = nci * TAPS;  // contiguous floats per output channel in this tile
   const int tid = threadIdx.x;
@@ -69,6 +68,30 @@ pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
             tile[col][cil * TAPS + t];
     }
   }
+}
+
+template <int TAPS, bool FULL>
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
+                   __nv_bfloat16* __restrict__ dgrad, int Cout, int Cin,
+                   const float* __restrict__ out_scale) {
+  __shared__ __nv_bfloat16 tile[kPackT][kPackT * 9 + 2];
+  pack_tile<TAPS, FULL>(w, fwd, dgrad, Cout, Cin, out_scale, blockIdx.x, blockIdx.y, tile);
+}
+
+// Every conv weight of the network in one launch (the packs are rebuilt once per optimizer step):
+// desc[t] = {w, fwd, dgrad, Cout, Cin, taps} as int64, blocks[b] = {tensor, ci tile, co tile, -}.
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const long long* __restrict__ desc, const int4* __restrict__ blocks) {
+  __shared__ __nv_bfloat16 tile[kPackT][kPackT * 9 + 2];
+  const int4 b = blocks[blockIdx.x];
+  const long long* d = desc + 6 * b.x;
+  const float* w = reinterpret_cast<const float*>(d[0]);
+  __nv_bfloat16* fwd = reinterpret_cast<__nv_bfloat16*>(d[1]);
+  __nv_bfloat16* dgrad = reinterpret_cast<__nv_bfloat16*>(d[2]);
+  const int Cout = static_cast<int>(d[3]), Cin = static_cast<int>(d[4]);
+  if (d[5] == 9) pack_tile<9, true>(w, fwd, dgrad, Cout, Cin, nullptr, b.y, b.z, tile);
+  else pack_tile<1, true>(w, fwd, dgrad, Cout, Cin, nullptr, b.y, b.z, tile);
 }
 
 // Stage 1 of the split-K fold when there are many splits: partial[0][i] = sum_s partial[s][i],
@@ -159,6 +182,13 @@ int ub2_pack_conv_weight(const float* w, void* fwd, void* dgrad, int Cout, int C
   else if (taps == 9) pack_weight_kernel<9, false><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
   else if (full) pack_weight_kernel<1, true><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
   else pack_weight_kernel<1, false><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_pack_conv_weights_multi(const long long* desc, const int* blocks, int nblocks, void* stream) {
+  if (nblocks <= 0) return UB2_ERR_SHAPE;
+  pack_weights_multi_kernel<<<nblocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      desc, reinterpret_cast<const int4*>(blocks));
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -130,6 +130,45 @@ def pack_conv_weight(w, want_fwd=True, want_dgrad=True, out_scale=None):
     return fwd, dg
 
 
+class WeightPacker:
+    """bf16 packs of many conv weights rebuilt by ONE launch (``ub2_pack_conv_weights_multi``).
+
+    The packs only change when the optimizer steps, so a training step rebuilds them once at its
+    start instead of launching a small kernel per layer inside forward.  ``get(w)`` returns the
+    (forward, data-gradient) packs of a registered weight or None."""
+
+    def __init__(self, weights):
+        self.entries = {}
+        desc, blocks = [], []
+        for w in weights:
+            cout, cin, kh, kw = w.shape
+            taps = kh * kw
+            if not (w.is_cuda and w.dtype == F32 and w.is_contiguous() and cout % 16 == 0 and cin % 16 == 0
+                    and taps in (1, 9)) or id(w) in self.entries:
+                continue
+            fwd = torch.empty((cout, taps, cin), device=w.device, dtype=BF16)
+            dg = torch.empty((cin, taps, cout), device=w.device, dtype=BF16)
+            t = len(desc)
+            desc.append([w.data_ptr(), fwd.data_ptr(), dg.data_ptr(), cout, cin, taps])
+            blocks += [[t, ci, co, 0] for co in range(cout // 16) for ci in range(cin // 16)]
+            self.entries[id(w)] = (w, w.data_ptr(), fwd, dg)
+        self.nblocks = len(blocks)
+        if self.nblocks:
+            dev = next(iter(self.entries.values()))[0].device
+            self.desc = torch.tensor(desc, dtype=torch.int64).to(dev)
+            self.blocks = torch.tensor(blocks, dtype=torch.int32).to(dev)
+
+    def run(self):
+        if self.nblocks:
+            _C.call("ub2_pack_conv_weights_multi", ptr(self.desc), ptr(self.blocks), self.nblocks, stream())
+
+    def get(self, w):
+        e = self.entries.get(id(w))
+        if e is None or e[0] is not w or e[1] != w.data_ptr():
+            return None
+        return e[2], e[3]
+
+
 # --------------------------------------------------------------------------- batch norm
 def bn_finalize(partials, count, gamma, beta, running_mean, running_var, nbt, momentum, eps):
     """Per-CTA sums -> (scale, shift, mean, invstd); updates the running buffers in place."""

@@ -44,6 +44,19 @@ def _grads_done(*params):
         GRAD_SINK(p)
 
 
+# Weight packs prepared for the current step by a ``kernels.WeightPacker`` (installed by
+# BatchShardedTrainer after it has rebuilt them in one launch); None -> pack per call.
+PACKS = None
+
+
+def _packs(weight, want_dgrad):
+    if PACKS is not None:
+        hit = PACKS.get(weight)
+        if hit is not None:
+            return hit
+    return K.pack_conv_weight(weight, True, want_dgrad)
+
+
 def to_nhwc(x: torch.Tensor) -> torch.Tensor:
     """Logical NCHW tensor -> dense NHWC bf16 view (no copy if already channels_last bf16)."""
     if not x.is_cuda:
@@ -93,7 +106,7 @@ class ConvBnRelu(torch.autograd.Function):
         taps = weight.shape[2] * weight.shape[3]
         need_grad = any(ctx.needs_input_grad)
         need_dx = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        wf, wd = K.pack_conv_weight(weight, True, need_dx)
+        wf, wd = _packs(weight, need_dx)
         batch = _use_batch_stats(bn)
         if not batch and not need_grad:
             # inference: BatchNorm folded into the conv epilogue, ReLU fused
@@ -231,8 +244,8 @@ class AttentionGateFn(torch.autograd.Function):
         n, h, w, cx = xn.shape
         count = n * h * w
         need_grad = any(ctx.needs_input_grad)
-        wgf, wgd = K.pack_conv_weight(w_g, True, need_grad)
-        wxf, wxd = K.pack_conv_weight(w_x, True, need_grad)
+        wgf, wgd = _packs(w_g, need_grad)
+        wxf, wxd = _packs(w_x, need_grad)
         wpsi = w_psi.reshape(-1)
         batch = _use_batch_stats(bn_x)
         q = K.conv_fwd(gn, wgf, 1)

@@ -53,6 +53,7 @@ class BatchShardedTrainer:
         self._bucket_of = {}
         self._build_buckets(bucket_mb)
         self._steps = 0
+        self._packer = None   # all bf16 weight packs of the model, rebuilt by one launch per step
         # CUDA-graph replay of the whole step: a 512^2 batch-4 step is ~800 kernel launches, more
         # host time than GPU time when issued one by one.  Every kernel of the path is
         # stream-ordered with no host synchronisation, so the step is captured once per input
@@ -111,13 +112,21 @@ class BatchShardedTrainer:
             b.flat.zero_()
             b.pending = len(b.params)
             b.work = None
-        outputs = self.model(images)
-        loss = self.criterion(outputs, masks)
-        prev_sink, ops.GRAD_SINK = ops.GRAD_SINK, self._grad_sink
+        dev = next(self.model.parameters()).device
+        if dev.type == "cuda":
+            if self._packer is None:
+                from .kernels import WeightPacker
+                self._packer = WeightPacker([m.weight for m in self.model.modules()
+                                             if isinstance(m, torch.nn.Conv2d) and m.weight.is_cuda])
+            self._packer.run()
+        prev_sink, prev_packs = ops.GRAD_SINK, ops.PACKS
+        ops.GRAD_SINK, ops.PACKS = self._grad_sink, self._packer
         try:
+            outputs = self.model(images)
+            loss = self.criterion(outputs, masks)
             (loss / self.world).backward()
         finally:
-            ops.GRAD_SINK = prev_sink
+            ops.GRAD_SINK, ops.PACKS = prev_sink, prev_packs
         if self.world > 1:
             for b in self.buckets:
                 if b.work is None:  # a parameter without gradient this step
