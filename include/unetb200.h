@@ -69,6 +69,17 @@ int ub2_conv_wgrad(const void* in0, int ld_in0, int C0, const void* in1, int ld_
 int ub2_wgrad_reduce(float* partial, int splits, int Cout, int Cin, int taps, float* grad,
                      int accumulate, void* stream);
 
+/* The same fold for up to UB2_REDUCE_MAX_ITEMS layers in one or two launches (one gradient bucket
+ * at a time instead of one or two launches per layer).  `items` is a HOST array read during the
+ * call; it is passed to the kernels by value, so the launch can be captured into a CUDA graph. */
+#define UB2_REDUCE_MAX_ITEMS 32
+typedef struct Ub2ReduceItem {
+  float* partial; /* (splits, taps*Cin, Cout) fp32, scratch */
+  float* grad;    /* (Cout, Cin, k, k) fp32 */
+  int splits, Cout, Cin, taps;
+} Ub2ReduceItem;
+int ub2_wgrad_reduce_multi(const Ub2ReduceItem* items, int n, int accumulate, void* stream);
+
 /* OIHW fp32 parameter -> bf16 packs: fwd (Cout,taps,Cin) and dgrad (Cin,taps flipped,Cout);
  * either may be NULL; out_scale (optional, per Cout) folds a BatchNorm scale into the pack. */
 int ub2_pack_conv_weight(const float* w, void* fwd, void* dgrad, int Cout, int Cin, int taps,

@@ -191,3 +191,23 @@ def test_weight_packer_multi():
         rf, rd = K.pack_conv_weight(w, True, True)
         assert torch.equal(fwd, rf) and torch.equal(dg, rd)
     assert packer.get(ws[0].clone()) is None
+
+
+def test_wgrad_reduce_multi():
+    """Several layers folded by one call == the per-layer fold (both split regimes, both tap counts)."""
+    from unet import kernels as K
+
+    g = torch.Generator().manual_seed(9)
+    shapes = [(64, 64, 9, 37), (128, 64, 9, 4), (32, 64, 1, 12), (256, 512, 9, 2), (48, 80, 9, 9), (16, 16, 1, 1)]
+    items, refs = [], []
+    for cout, cin, taps, splits in shapes:
+        k = 3 if taps == 9 else 1
+        part = torch.randn(splits, taps * cin, cout, generator=g).cuda()
+        base = torch.randn(cout, cin, k, k, generator=g).cuda()
+        ref = K.wgrad_reduce(part.clone(), cout, cin, taps, base.clone(), accumulate=True)
+        tgt = base.clone()
+        items.append((part, cout, cin, taps, tgt))
+        refs.append(ref)
+    K.wgrad_reduce_multi(items, accumulate=True)
+    for (_, _, _, _, tgt), ref in zip(items, refs):
+        assert torch.equal(tgt, ref)

@@ -21,17 +21,17 @@ namespace ub2 {
 static constexpr int kBnThreads = 256;
 
 // ------------------------------------------------------------------------------ finalize
-// blockDim = (32, 32): see rows_sum in vec.cuh
+// blockDim = (8, 128): see rows_sum_wide in vec.cuh
 __global__ void bn_finalize_kernel(const double* __restrict__ partials, int rows, int C, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, long long* nbt,
                                    float momentum, float eps, float* scale, float* shift, float* mean,
                                    float* invstd) {
-  __shared__ double smem[2 * 32 * 33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double smem[2 * 128 * 9];
+  const int c = blockIdx.x * 8 + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && nbt != nullptr) *nbt += 1;
   double s[2];
-  rows_sum<2>(partials, rows, C, c, s, smem);
+  rows_sum_wide<2>(partials, rows, C, c, s, smem);
   if (threadIdx.y != 0 || c >= C) return;
   const double m = s[0] / count;
   double var = s[1] / count - m * m;
@@ -288,10 +288,10 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partials, int 
                                        double count, const float* __restrict__ gamma,
                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                        int frozen, float* dgamma, float* dbeta, float* coef) {
-  __shared__ double smem[2 * 32 * 33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double smem[2 * 128 * 9];
+  const int c = blockIdx.x * 8 + threadIdx.x;
   double s[2];
-  rows_sum<2>(partials, rows, C, c, s, smem);
+  rows_sum_wide<2>(partials, rows, C, c, s, smem);
   if (threadIdx.y != 0 || c >= C) return;
   const double mu = mean[c], is = invstd[c];
   const double db = s[0];
@@ -320,7 +320,7 @@ int ub2_bn_finalize(const double* partials, int rows, int C, double count, const
                     float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
                     void* stream) {
   if (C <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_finalize_kernel<<<(C + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream)>>>(
       partials, rows, C, count, gamma, beta, running_mean, running_var, nbt, momentum, eps, scale,
       shift, mean, invstd);
   return static_cast<int>(cudaGetLastError());
@@ -385,7 +385,7 @@ int ub2_bn_bwd_finalize(const double* partials, int rows, int C, double count, c
                         const float* mean, const float* invstd, int frozen, float* dgamma, float* dbeta,
                         float* coef, void* stream) {
   if (C <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream)>>>(
       partials, rows, C, count, gamma, mean, invstd, frozen, dgamma, dbeta, coef);
   return static_cast<int>(cudaGetLastError());
 }

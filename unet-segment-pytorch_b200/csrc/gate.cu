@@ -316,7 +316,7 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
 
 // Raw sums -> parameter gradients and the backward coefficients of the two BatchNorms:
 //   dxp = coef0*ds + coef1*xp + coef2 ;  d(up q) = coef3*ds + coef4*up(q) + coef5
-// blockDim = (32, 32): see rows_sum in vec.cuh
+// blockDim = (8, 128): see rows_sum_wide in vec.cuh
 __global__ void gate_bwd_finalize_kernel(const double* __restrict__ partials, int rows, int C,
                                          double count, const float* __restrict__ gamma_x,
                                          const float* __restrict__ mean_x,
@@ -326,10 +326,10 @@ __global__ void gate_bwd_finalize_kernel(const double* __restrict__ partials, in
                                          const float* __restrict__ invstd_g, int frozen, float* dgamma_x,
                                          float* dbeta_x, float* dgamma_g, float* dbeta_g, float* dwpsi,
                                          float* coef) {
-  __shared__ double smem[4 * 32 * 33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double smem[4 * 128 * 9];
+  const int c = blockIdx.x * 8 + threadIdx.x;
   double s[4];
-  rows_sum<4>(partials, rows, C, c, s, smem);
+  rows_sum_wide<4>(partials, rows, C, c, s, smem);
   if (threadIdx.y != 0 || c >= C) return;
   const double mx = mean_x[c], ix = invstd_x[c], mg = mean_g[c], ig = invstd_g[c];
   const double db = s[0];
@@ -503,7 +503,7 @@ int ub2_gate_bwd_finalize(const double* partials, int rows, int Ci, double count
                           float* dbeta_x, float* dgamma_g, float* dbeta_g, float* dwpsi, float* coef,
                           void* stream) {
   if (Ci <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  gate_bwd_finalize_kernel<<<(Ci + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
+  gate_bwd_finalize_kernel<<<(Ci + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream)>>>(
       partials, rows, Ci, count, gamma_x, mean_x, invstd_x, gamma_g, mean_g, invstd_g, frozen, dgamma_x,
       dbeta_x, dgamma_g, dbeta_g, dwpsi, coef);
   return static_cast<int>(cudaGetLastError());

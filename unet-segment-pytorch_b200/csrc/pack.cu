@@ -130,11 +130,10 @@ wgrad_presum_kernel(float* __restrict__ partial, int splits, long long quads) {
 static constexpr int kRedCi = 8;
 
 template <int TAPS>
-__global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin,
-                    float* __restrict__ grad, int accumulate) {
-  __shared__ float tile[32][kRedCi * TAPS + 1];
-  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * kRedCi;
+__device__ __forceinline__ void reduce_tile(const float* __restrict__ partial, int splits, int Cout, int Cin,
+                                            float* __restrict__ grad, int accumulate, int co_tile,
+                                            int ci_tile, float (*tile)[kRedCi * 9 + 1]) {
+  const int co0 = co_tile * 32, ci0 = ci_tile * kRedCi;
   const int nci = min(kRedCi, Cin - ci0);
   const size_t total = static_cast<size_t>(Cout) * Cin * TAPS;
   const int co = co0 + threadIdx.x;
@@ -162,6 +161,70 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int
   }
 }
 
+template <int TAPS>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin,
+                    float* __restrict__ grad, int accumulate) {
+  __shared__ float tile[32][kRedCi * 9 + 1];
+  reduce_tile<TAPS>(partial, splits, Cout, Cin, grad, accumulate, blockIdx.x, blockIdx.y, tile);
+}
+
+// Several layers per launch (one launch per gradient bucket instead of one or two per layer).
+// The item table travels as a kernel argument, so the launch can sit in a captured graph.
+struct ReduceItems {
+  Ub2ReduceItem item[UB2_REDUCE_MAX_ITEMS];
+  int first_block[UB2_REDUCE_MAX_ITEMS + 1];
+  int n;
+};
+
+__device__ __forceinline__ int find_item(const ReduceItems& t, int block) {
+  int i = 0;
+  while (i + 1 < t.n && block >= t.first_block[i + 1]) ++i;
+  return i;
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_presum_multi_kernel(const __grid_constant__ ReduceItems t) {
+  __shared__ float4 s_red[8][32];
+  const int i = find_item(t, blockIdx.x);
+  const Ub2ReduceItem& it = t.item[i];
+  const long long quads = static_cast<long long>(it.Cout) * it.Cin * it.taps / 4;
+  const long long q = static_cast<long long>(blockIdx.x - t.first_block[i]) * 32 + threadIdx.x;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < quads) {
+    const float4* src = reinterpret_cast<const float4*>(it.partial) + q;
+#pragma unroll 4
+    for (int s = threadIdx.y; s < it.splits; s += 8) {
+      const float4 v = src[static_cast<size_t>(s) * quads];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  s_red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && q < quads) {
+    float4 r = s_red[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < 8; ++y) {
+      const float4 v = s_red[y][threadIdx.x];
+      r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+    }
+    reinterpret_cast<float4*>(it.partial)[q] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_reduce_multi_kernel(const __grid_constant__ ReduceItems t, int accumulate) {
+  __shared__ float tile[32][kRedCi * 9 + 1];
+  const int i = find_item(t, blockIdx.x);
+  const Ub2ReduceItem& it = t.item[i];
+  const int local = blockIdx.x - t.first_block[i];
+  const int co_tiles = (it.Cout + 31) / 32;
+  if (it.taps == 9)
+    reduce_tile<9>(it.partial, it.splits, it.Cout, it.Cin, it.grad, accumulate, local % co_tiles, local / co_tiles, tile);
+  else
+    reduce_tile<1>(it.partial, it.splits, it.Cout, it.Cin, it.grad, accumulate, local % co_tiles, local / co_tiles, tile);
+}
+
 }  // namespace ub2
 
 using namespace ub2;
@@ -182,6 +245,35 @@ int ub2_pack_conv_weight(const float* w, void* fwd, void* dgrad, int Cout, int C
   else if (taps == 9) pack_weight_kernel<9, false><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
   else if (full) pack_weight_kernel<1, true><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
   else pack_weight_kernel<1, false><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_wgrad_reduce_multi(const Ub2ReduceItem* items, int n, int accumulate, void* stream) {
+  if (n <= 0 || n > UB2_REDUCE_MAX_ITEMS) return UB2_ERR_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ReduceItems pre{}, red{};
+  int pre_blocks = 0, red_blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    const Ub2ReduceItem& it = items[i];
+    if (it.Cout <= 0 || it.Cin <= 0 || it.splits <= 0 || (it.taps != 1 && it.taps != 9)) return UB2_ERR_SHAPE;
+    const long long total = static_cast<long long>(it.Cout) * it.Cin * it.taps;
+    Ub2ReduceItem r = it;
+    if (it.splits > 8 && total % 4 == 0) {   // many splits: column sums first, all SMs busy
+      pre.item[pre.n] = it;
+      pre.first_block[pre.n] = pre_blocks;
+      pre_blocks += static_cast<int>((total / 4 + 31) / 32);
+      ++pre.n;
+      r.splits = 1;
+    }
+    red.item[i] = r;
+    red.first_block[i] = red_blocks;
+    red_blocks += ((it.Cout + 31) / 32) * ((it.Cin + kRedCi - 1) / kRedCi);
+  }
+  red.n = n;
+  pre.first_block[pre.n] = pre_blocks;
+  red.first_block[n] = red_blocks;
+  if (pre.n > 0) wgrad_presum_multi_kernel<<<pre_blocks, dim3(32, 8), 0, st>>>(pre);
+  wgrad_reduce_multi_kernel<<<red_blocks, dim3(32, kRedCi), 0, st>>>(red, accumulate);
   return static_cast<int>(cudaGetLastError());
 }
 

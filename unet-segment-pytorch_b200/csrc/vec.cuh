@@ -97,6 +97,39 @@ __device__ __forceinline__ void rows_sum(const double* __restrict__ partials, in
   }
 }
 
+// The same reduction for blockDim = (8, 128): 8 channels per block (grid = ceil(C / 8)), 128 row
+// lanes, so a few hundred rows are one or two independent loads per thread followed by a
+// shared-memory tree — the latency of these tiny kernels is what they cost.  Fixed order.
+template <int NS>
+__device__ __forceinline__ void rows_sum_wide(const double* __restrict__ partials, int rows, int C, int c,
+                                              double (&out)[NS], double* smem /* [NS][128][9] */) {
+  double acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+  if (c < C) {
+#pragma unroll 4
+    for (int r = threadIdx.y; r < rows; r += 128) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) acc[k] += partials[(static_cast<size_t>(r) * NS + k) * C + c];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NS; ++k) smem[(k * 128 + threadIdx.y) * 9 + threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int s = 64; s >= 1; s >>= 1) {
+    if (threadIdx.y < s) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k)
+        smem[(k * 128 + threadIdx.y) * 9 + threadIdx.x] += smem[(k * 128 + threadIdx.y + s) * 9 + threadIdx.x];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) out[k] = smem[(k * 128) * 9 + threadIdx.x];
+  }
+}
+
 // Grid for a bandwidth-bound grid-stride kernel: a multiple of the SM count.
 inline int stream_grid(long long work_items, int threads, int sms, int blocks_per_sm = 8) {
   long long need = (work_items + threads - 1) / threads;

@@ -8,6 +8,8 @@ step can be captured into a CUDA graph.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _C
@@ -117,6 +119,23 @@ def wgrad_reduce(partial, cout, cin, taps, grad, accumulate=False):
     _C.call("ub2_wgrad_reduce", ptr(partial), partial.shape[0], cout, cin, taps, ptr(grad), int(accumulate),
             stream())
     return grad
+
+
+class _ReduceItem(ctypes.Structure):
+    _fields_ = [("partial", ctypes.c_void_p), ("grad", ctypes.c_void_p), ("splits", ctypes.c_int),
+                ("Cout", ctypes.c_int), ("Cin", ctypes.c_int), ("taps", ctypes.c_int)]
+
+
+def wgrad_reduce_multi(items, accumulate=True):
+    """Fold the split-K partials of several layers in one or two launches.
+    ``items``: (partial, cout, cin, taps, grad) tuples; see ``wgrad_reduce``."""
+    for i in range(0, len(items), 32):
+        chunk = items[i:i + 32]
+        arr = (_ReduceItem * len(chunk))()
+        for j, (partial, cout, cin, taps, grad) in enumerate(chunk):
+            assert grad.dtype == F32 and grad.is_contiguous() and partial.is_contiguous()
+            arr[j] = _ReduceItem(partial.data_ptr(), grad.data_ptr(), partial.shape[0], cout, cin, taps)
+        _C.call("ub2_wgrad_reduce_multi", arr, len(chunk), int(accumulate), stream())
 
 
 def pack_conv_weight(w, want_fwd=True, want_dgrad=True, out_scale=None):

@@ -44,6 +44,17 @@ def _grads_done(*params):
         GRAD_SINK(p)
 
 
+def _reduce_into(param, partial, cout, cin, taps, target):
+    """Fold split-K partials into ``target`` (+=): right away, or — if the sink batches them —
+    handed over to be folded together with the other layers of the same gradient bucket."""
+    defer = getattr(GRAD_SINK, "defer_reduce", None)
+    if defer is not None:
+        defer(param, (partial, cout, cin, taps, target))
+    else:
+        K.wgrad_reduce(partial, cout, cin, taps, target, accumulate=True)
+        GRAD_SINK(param)
+
+
 # Weight packs prepared for the current step by a ``kernels.WeightPacker`` (installed by
 # BatchShardedTrainer after it has rebuilt them in one launch); None -> pack per call.
 PACKS = None
@@ -149,8 +160,7 @@ class ConvBnRelu(torch.autograd.Function):
             part = K.conv_wgrad(a0, dy, taps, x1=a1)
             w_t = _grad_targets(p_w)
             if w_t is not None:
-                K.wgrad_reduce(part, cout, cin, taps, w_t[0], accumulate=True)
-                _grads_done(p_w)
+                _reduce_into(p_w, part, cout, cin, taps, w_t[0])
             else:
                 gw = torch.empty(wshape, device=dy.device, dtype=torch.float32)
                 K.wgrad_reduce(part, cout, cin, taps, gw)
@@ -294,8 +304,8 @@ class AttentionGateFn(torch.autograd.Function):
         dxp, dgup = K.gate_bwd_xg(ds, xp, q, coef)
         dq = K.upsample_bwd(dgup, hin, win, h, w)
         if direct is not None:
-            K.wgrad_reduce(K.conv_wgrad(xn, dxp, 1), ci, cx, 1, t_wx, accumulate=True)
-            K.wgrad_reduce(K.conv_wgrad(gn, dq, 1), ci, cg, 1, t_wg, accumulate=True)
+            _reduce_into(p_wx, K.conv_wgrad(xn, dxp, 1), ci, cx, 1, t_wx)
+            _reduce_into(p_wg, K.conv_wgrad(gn, dq, 1), ci, cg, 1, t_wg)
         else:
             gw_x = torch.empty(sh_x, device=d.device, dtype=torch.float32)
             K.wgrad_reduce(K.conv_wgrad(xn, dxp, 1), ci, cx, 1, gw_x)
@@ -304,7 +314,7 @@ class AttentionGateFn(torch.autograd.Function):
         K.conv_fwd(dxp, wxd, 1, out=dx, accumulate=True)
         dg = K.conv_fwd(dq, wgd, 1)
         if direct is not None:
-            _grads_done(*ctx.params)
+            _grads_done(*ctx.params[2:])   # the two projection weights were reported by _reduce_into
             return (from_nhwc(dg), from_nhwc(dx)) + (None,) * 12
         return (from_nhwc(dg), from_nhwc(dx), gw_g, gw_x, grads[4].reshape(sh_p), grads[2], grads[3],
                 grads[0], grads[1], dgam_p, dbet_p, None, None, None)

@@ -27,10 +27,24 @@ from .optim import FusedAdamW
 
 
 class _Bucket:
-    __slots__ = ("flat", "params", "pending", "work")
+    __slots__ = ("flat", "params", "pending", "work", "deferred")
 
     def __init__(self, flat, params):
         self.flat, self.params, self.pending, self.work = flat, params, 0, None
+        self.deferred = []   # split-K folds of this bucket's conv weights, launched together
+
+
+class _GradSink:
+    """What unet.ops talks to during the trainer's backward pass (see ops.GRAD_SINK)."""
+
+    def __init__(self, trainer):
+        self.trainer = trainer
+
+    def __call__(self, param):
+        self.trainer._grad_sink(param)
+
+    def defer_reduce(self, param, item):
+        self.trainer._defer_reduce(param, item)
 
 
 class BatchShardedTrainer:
@@ -90,10 +104,34 @@ class BatchShardedTrainer:
                 if self.world > 1:
                     p.register_post_accumulate_grad_hook(self._make_hook(b))
 
-    def _bucket_ready(self, bucket: _Bucket) -> None:
-        bucket.pending -= 1
-        if bucket.pending == 0 and self.world > 1:
+    def _bucket_ready(self, bucket: _Bucket, n: int = 1) -> None:
+        bucket.pending -= n
+        if bucket.deferred and bucket.pending == len(bucket.deferred):
+            # every other gradient of the bucket is in: fold all its split-K partials in one go
+            from .kernels import wgrad_reduce_multi
+            items, bucket.deferred = bucket.deferred, []
+            wgrad_reduce_multi(items, accumulate=True)
+            bucket.pending -= len(items)
+        if bucket.pending == 0 and self.world > 1 and bucket.work is None:
             bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _defer_reduce(self, param, item) -> None:
+        b = self._bucket_of.get(id(param))
+        if b is None:   # not one of ours: fold it now
+            from .kernels import wgrad_reduce
+            wgrad_reduce(*item, accumulate=True)
+            return
+        b.deferred.append(item)
+        self._bucket_ready(b, 0)
+
+    def _flush_deferred(self) -> None:
+        """End of backward: buckets in which some parameter received no gradient this step."""
+        from .kernels import wgrad_reduce_multi
+        for b in self.buckets:
+            if b.deferred:
+                items, b.deferred = b.deferred, []
+                wgrad_reduce_multi(items, accumulate=True)
+                b.pending -= len(items)
 
     def _make_hook(self, bucket: _Bucket):
         return lambda _param: self._bucket_ready(bucket)
@@ -112,6 +150,7 @@ class BatchShardedTrainer:
             b.flat.zero_()
             b.pending = len(b.params)
             b.work = None
+            b.deferred = []
         dev = next(self.model.parameters()).device
         if dev.type == "cuda":
             if self._packer is None:
@@ -120,11 +159,12 @@ class BatchShardedTrainer:
                                              if isinstance(m, torch.nn.Conv2d) and m.weight.is_cuda])
             self._packer.run()
         prev_sink, prev_packs = ops.GRAD_SINK, ops.PACKS
-        ops.GRAD_SINK, ops.PACKS = self._grad_sink, self._packer
+        ops.GRAD_SINK, ops.PACKS = _GradSink(self), self._packer
         try:
             outputs = self.model(images)
             loss = self.criterion(outputs, masks)
             (loss / self.world).backward()
+            self._flush_deferred()
         finally:
             ops.GRAD_SINK, ops.PACKS = prev_sink, prev_packs
         if self.world > 1:
