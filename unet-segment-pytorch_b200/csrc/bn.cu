@@ -79,7 +79,7 @@ static WinGeom make_geom(int N, int H, int W, int C) {
 }
 
 // ------------------------------------------------------------------------------ forward apply
-__global__ void __launch_bounds__(kBnThreads)
+__global__ void __launch_bounds__(kBnThreads, 4)
 bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __restrict__ scale,
               const float* __restrict__ shift, __nv_bfloat16* a, int ld_a, __nv_bfloat16* pooled,
               int ld_p, unsigned char* pidx, int relu, WinGeom g) {
@@ -105,12 +105,24 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __rest
     for (int i = 0; i < 8; ++i) arg[i] = 0u;
 #pragma unroll
     for (int i = 0; i < 8; ++i) mx.v[i] = -INFINITY;
+    // the window's four 128-bit loads are in flight together (kept packed: 16 registers); with a
+    // load -> store chain per pixel the kernel is latency bound at ~4.4 TB/s
+    uint4 raw[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int h = hc * 2 + (d >> 1), w = wc * 2 + (d & 1);
+      raw[d] = make_uint4(0u, 0u, 0u, 0u);
+      if (h < g.H && w < g.W) {
+        const size_t pix = (static_cast<size_t>(n) * g.H + h) * g.W + w;
+        raw[d] = ld_stream16(y + pix * ld_y + cg * 8);
+      }
+    }
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
       const int h = hc * 2 + (d >> 1), w = wc * 2 + (d & 1);
       if (h < g.H && w < g.W) {
         const size_t pix = (static_cast<size_t>(n) * g.H + h) * g.W + w;
-        F8 v = load8_stream(y + pix * ld_y + cg * 8);
+        F8 v = unpack8(raw[d]);
         uint4 packed;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
