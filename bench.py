@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set()
@@ -162,6 +162,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner)
+    # goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a B200: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
@@ -279,7 +284,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     _shutdown(trainer, world)
 
 
