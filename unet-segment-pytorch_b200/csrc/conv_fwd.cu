@@ -254,6 +254,13 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   if (a.out1 != nullptr) {
     if (a.split % 8 != 0 || a.ld1 % 8 != 0) return UB2_ERR_ALIGN;
   }
+  {
+    // few pixel tiles (deep layers at small batch): halve the N tile so that the grid covers the SMs
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    while (BN > 64 && BN % 32 == 0 && a.Cout % (BN / 2) == 0 && (split == (1 << 30) || split % (BN / 2) == 0) &&
+           m_tiles * ((a.Cout + BN - 1) / BN) * 2 <= num_sms())
+      BN /= 2;
+  }
   if (a.bn_override > 0) BN = a.bn_override;
   if (BN % 16 != 0 || BN > 256) return UB2_ERR_SHAPE;
   p.BN = BN;
