@@ -253,9 +253,19 @@ def run_ours(args):
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     conv_ms_per_step = conv_ms / prof_steps
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-    roofline = {"bound": "tensor", "kernel": "conv_fwd_kernel (3x3/1x1 forward + data-gradient implicit GEMM)",
+    traffic, traffic_note = None, None
+    try:   # DRAM bytes per launch of the same kernels from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["traffic_bytes_per_launch"]
+        traffic_note = (f"mean dram__bytes_read+write per launch, {tj['source']}; algorithmic operand bytes of the "
+                        f"same launches: {tj['algorithmic_bytes_per_launch']:.3e}")
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "conv_fwd_kernel / conv_halo_kernel (3x3 and 1x1 forward + "
+                                             "data-gradient implicit GEMM, tcgen05)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a step)",
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a step)",
                 "launches_per_step": len(prof) // prof_steps, "kernel_ms_per_step": conv_ms_per_step,
                 "share_of_step": conv_ms_per_step / (ms / args.steps),
                 "how": "CUDA events around every launch in an eager pass of the same step "
