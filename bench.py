@@ -115,8 +115,14 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 1
-    ips, cores, per = cpu_train_step_throughput(batch, max(1, args.steps), max(0, min(args.warmup, 1)))
+    # the arm's workload is ours (batch 4 per step); if K steps of it would not finish within a few
+    # minutes on this host, each step becomes a bounded sample (fewer images of the same shape)
+    steps = max(1, args.steps)
+    probe_ips, _, _ = cpu_train_step_throughput(1, 1, 0)
+    batch = 4
+    while batch > 1 and steps * batch / probe_ips > 240.0:
+        batch //= 2
+    ips, cores, per = cpu_train_step_throughput(batch, steps, max(0, min(args.warmup, 1)))
     sample = f"fp32 CPU train step (fwd+DiceBCE+bwd+clip+AdamW), batch {batch}x1x512x512 per step, {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
@@ -273,9 +279,10 @@ def run_ours(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ips, cores, per = cpu_train_step_throughput(2, 1, 0)
+        ips, cores, per = cpu_train_step_throughput(4, 3, 1)
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"one fp32 CPU train step of the oracle, batch 2x1x512x512 ({per:.1f} s), {cores} threads"}
+               "sample": f"3 timed (+1 warm-up) fp32 CPU train steps of the oracle on the same workload, batch "
+                         f"4x1x512x512 ({per:.1f} s/step), {cores} threads"}
 
     total_imgs = B * world * args.steps
     line = {
