@@ -207,6 +207,33 @@ int ub2_confusion(const void* pred, const long long* target, int mode, int N, in
                   long long ignore_index, int has_ignore, float threshold, long long* cm,
                   unsigned char* mask_out, void* stream);
 
+/* ======================= fp32 / TF32 evaluation mode ==================================== */
+
+/* BASELINE configs[0] (AttentionUNet fp32 forward) and north_star's "fp32/TF32 mode, logits within
+ * 1e-3": the eval-mode forward of every block of unet/models/layers.py with fp32 NHWC activations
+ * (element strides), BatchNorm folded with the running statistics, the 3x3 / 1x1 convolutions on
+ * the tensor cores as kind::tf32.  Forward only. */
+/* nn.Conv2d (+ folded BN + ReLU) of layers.py:32-37,152,158: in0/in1 fp32 NHWC (virtual concat),
+ * wgt = ub2_f32_pack_weight output (Cout,taps,C0+C1) fp32, out fp32 NHWC; out = relu?(scale*acc+shift). */
+int ub2_conv_fwd_tf32(const float* in0, int ld_in0, int C0, const float* in1, int ld_in1, int C1,
+                      const float* wgt, float* out, int ld_out, int N, int H, int W, int Cout, int taps,
+                      const float* scale, const float* shift, int relu, void* stream);
+int ub2_f32_pack_weight(const float* w, float* out, int Cout, int Cin, int taps, void* stream);
+/* first conv + folded BN + ReLU: x fp32 NCHW -> out fp32 NHWC (layers.py:32-34, Cin = n_channels) */
+int ub2_f32_conv_in(const float* x, const float* w, const float* scale, const float* shift, float* out, int N,
+                    int Cin, int H, int W, int Cout, void* stream);
+int ub2_f32_maxpool(const float* in, float* out, int N, int H, int W, int C, void* stream);          /* layers.py:56 */
+int ub2_f32_upsample(const float* in, float* out, int N, int hin, int win, int hu, int wu, int Ho, int Wo, int C,
+                     void* stream);                                                              /* layers.py:78,98-102 */
+/* AttentionGate.forward after the two 1x1 projections q = W_g g (low resolution), xp = W_x x
+ * (layers.py:183-192): out = x * sigmoid(BN_psi(w_psi . relu(BN_g(up q) + BN_x(xp)))) */
+int ub2_f32_gate(const float* q, const float* xp, const float* x, const float* scale_g, const float* shift_g,
+                 const float* scale_x, const float* shift_x, const float* w_psi, const float* scale_psi,
+                 const float* shift_psi, float* out, int N, int hin, int win, int H, int W, int Ci, int Cx,
+                 void* stream);
+int ub2_f32_outc(const float* a, const float* w, const float* bias, float* logits, int N, int H, int W, int C,
+                 int K, void* stream);                                                           /* layers.py:120 */
+
 /* ======================= optimizer tail ================================== */
 
 /* torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm) (scripts/train.py:141) fused with

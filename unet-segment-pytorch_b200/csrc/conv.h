@@ -31,6 +31,7 @@ struct ConvFwdArgs {
   int accumulate, relu;
   int stats_rows;
   int bn_override, grid_override;  // tuning / tests; 0 = automatic
+  int tf32;  // fp32 NHWC activations, fp32 (Cout,taps,Cin) weights, fp32 output: kind::tf32 (eval only)
 };
 
 struct ConvFwdParams {
@@ -41,6 +42,7 @@ struct ConvFwdParams {
   __nv_bfloat16* out1;
   int ld0, ld1, split, accumulate, relu;
   int wide_store;  // 256-bit epilogue stores: pointers 32-byte aligned, ld / split multiples of 16
+  int tf32;        // fp32 operands / fp32 output (out0 is a float*)
   const float* scale;
   const float* shift;
   double* stats;
@@ -79,10 +81,10 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream);
 // ---- tensor maps -------------------------------------------------------------------------
 // NHWC bf16 activation viewed as a 4-D tensor {C, W, H, N}; box = {bc, bw, bh, bi}.
 int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int ld,
-                   const uint32_t box[4], int swizzle_bytes);
+                   const uint32_t box[4], int swizzle_bytes, int elem_bytes = 2);
 // Row-major bf16 matrix {cols (inner), rows}; box = {bc, br}.
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
-                 uint32_t bc, uint32_t br, int swizzle_bytes);
+                 uint32_t bc, uint32_t br, int swizzle_bytes, int elem_bytes = 2);
 int num_sms();
 
 inline int conv_wide_store_ok(const void* out0, int ld0, const void* out1, int ld1, int split, int Cout) {

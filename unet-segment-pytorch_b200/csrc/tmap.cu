@@ -31,17 +31,19 @@ static CUtensorMapSwizzle swizzle_mode(int bytes) {
 }
 
 int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int ld,
-                   const uint32_t box[4], int swizzle_bytes) {
+                   const uint32_t box[4], int swizzle_bytes, int elem_bytes) {
   std::call_once(g_once, resolve_encode);
   if (!g_encode) return UB2_ERR_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 8) != 0) return UB2_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * elem_bytes) % 16 != 0) return UB2_ERR_ALIGN;
+  const cuuint64_t eb = static_cast<cuuint64_t>(elem_bytes);
+  const CUtensorMapDataType dtype = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W),
                         static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(W) * ld * 2,
-                           static_cast<cuuint64_t>(H) * W * ld * 2};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * eb, static_cast<cuuint64_t>(W) * ld * eb,
+                           static_cast<cuuint64_t>(H) * W * ld * eb};
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+  CUresult r = g_encode(m, dtype, 4, const_cast<void*>(base), dims,
                         strides, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle_mode(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -49,15 +51,16 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C,
 }
 
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
-                 uint32_t bc, uint32_t br, int swizzle_bytes) {
+                 uint32_t bc, uint32_t br, int swizzle_bytes, int elem_bytes) {
   std::call_once(g_once, resolve_encode);
   if (!g_encode) return UB2_ERR_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 8) != 0) return UB2_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * elem_bytes) % 16 != 0) return UB2_ERR_ALIGN;
+  const CUtensorMapDataType dtype = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * static_cast<uint64_t>(elem_bytes)};
   cuuint32_t bx[2] = {bc, br};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+  CUresult r = g_encode(m, dtype, 2, const_cast<void*>(base), dims,
                         strides, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle_mode(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -6,7 +6,9 @@ hand-written sm_100a kernels from ``libunetb200.so``.
 """
 __version__ = "0.1.0"
 
+from .fp32 import set_precision
 from .models.layers import AttentionGate, AttentionUp, DoubleConv, Down, OutConv, Up
 from .models.unet import AttentionUNet, UNet
 
-__all__ = ["UNet", "AttentionUNet", "DoubleConv", "Down", "Up", "OutConv", "AttentionGate", "AttentionUp"]
+__all__ = ["UNet", "AttentionUNet", "DoubleConv", "Down", "Up", "OutConv", "AttentionGate", "AttentionUp",
+           "set_precision"]

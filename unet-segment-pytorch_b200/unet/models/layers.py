@@ -17,7 +17,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import fp32, ops
 
 
 def _stage(x0, x1, conv: nn.Conv2d, bn: nn.BatchNorm2d, pool: bool = False):
@@ -40,6 +40,8 @@ class DoubleConv(nn.Module):
         )
 
     def _run(self, x0, x1=None, pool_out: bool = False):
+        if fp32.active():
+            return fp32.double_conv(self, x0, x1, pool_out)
         seq = self.double_conv
         cin = x0.shape[1] + (x1.shape[1] if x1 is not None else 0)
         if cin % 16 != 0:
@@ -66,6 +68,8 @@ class Down(nn.Module):
         self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConv(in_channels, out_channels))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if fp32.active():
+            return self.maxpool_conv[1](fp32.maxpool(x))
         return self.maxpool_conv[1](ops.MaxPool2x2.apply(x))
 
     def forward_pooled(self, pooled: torch.Tensor, pool_out: bool):
@@ -87,6 +91,10 @@ class Up(nn.Module):
             self.conv = DoubleConv(in_channels, out_channels)
 
     def _upsampled(self, x1, skip):
+        if fp32.active():
+            if isinstance(self.up, nn.ConvTranspose2d):
+                raise NotImplementedError("TF32 mode supports bilinear=True only")
+            return fp32.upsample(x1, skip.shape[2], skip.shape[3])
         if isinstance(self.up, nn.ConvTranspose2d):
             return ops.conv_transpose2x2(x1, self.up.weight, self.up.bias, skip.shape[2], skip.shape[3])
         return ops.Upsample2x.apply(x1, skip.shape[2], skip.shape[3])
@@ -103,6 +111,8 @@ class OutConv(nn.Module):
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if fp32.active():
+            return fp32.outc(self, x)
         return ops.OutConvFn.apply(x, self.conv.weight, self.conv.bias)
 
 
@@ -121,6 +131,8 @@ class AttentionGate(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        if fp32.active():
+            return fp32.gate(self, g, x)
         bg, bx, bp = self.W_g[1], self.W_x[1], self.psi[1]
         return ops.AttentionGateFn.apply(g, x, self.W_g[0].weight, self.W_x[0].weight, self.psi[0].weight,
                                          bg.weight, bg.bias, bx.weight, bx.bias, bp.weight, bp.bias,
