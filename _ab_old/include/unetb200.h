@@ -196,15 +196,9 @@ int ub2_outc_bwd(const float* dlogits, const void* a, int ld_a, const float* w, 
 int ub2_seg_stats_blocks(int N, long long HW);
 int ub2_seg_stats(const float* logits, const long long* targets, int N, int C, long long HW,
                   double* partials, int blocks, float* stats, void* stream);
-/* dL/dlogits from coef (N,3,C) = {dL/dCE, dL/dI, dL/dP}, times *gscale (optional device scalar:
- * the upstream gradient of the loss). */
-int ub2_seg_stats_bwd(const float* logits, const long long* targets, const float* coef, const float* gscale,
-                      int N, int C, long long HW, float* dlogits, void* stream);
-/* DiceBCELoss.forward (unet/utils/loss.py:184-191, with :70-85 and :134-148) from the statistics:
- * loss (1) fp32 and the gradient table coef (N,3,C) for ub2_seg_stats_bwd, one launch. */
-int ub2_dice_bce_head(const float* stats, int N, int C, float ce_weight, float dice_weight, float class_weight,
-                      float ce_smooth, float dice_smooth, int ignore_background, float* loss, float* coef,
-                      void* stream);
+/* dL/dlogits from coef (N,3,C) = {dL/dCE, dL/dI, dL/dP}. */
+int ub2_seg_stats_bwd(const float* logits, const long long* targets, const float* coef, int N, int C,
+                      long long HW, float* dlogits, void* stream);
 /* SegmentationMetrics.update (unet/utils/metrics.py:55-84): cm ((C+1),(C+1)) int64 +=
  * histogram of (target, prediction); row/col C = ignored / out of range.  mode 0: argmax of
  * fp32 logits (N,C,H,W); 1: int64 class indices; 2: softmax[:,1] > threshold
@@ -212,33 +206,6 @@ int ub2_dice_bce_head(const float* stats, int N, int C, float ce_weight, float d
 int ub2_confusion(const void* pred, const long long* target, int mode, int N, int C, long long HW,
                   long long ignore_index, int has_ignore, float threshold, long long* cm,
                   unsigned char* mask_out, void* stream);
-
-/* ======================= fp32 / TF32 evaluation mode ==================================== */
-
-/* BASELINE configs[0] (AttentionUNet fp32 forward) and north_star's "fp32/TF32 mode, logits within
- * 1e-3": the eval-mode forward of every block of unet/models/layers.py with fp32 NHWC activations
- * (element strides), BatchNorm folded with the running statistics, the 3x3 / 1x1 convolutions on
- * the tensor cores as kind::tf32.  Forward only. */
-/* nn.Conv2d (+ folded BN + ReLU) of layers.py:32-37,152,158: in0/in1 fp32 NHWC (virtual concat),
- * wgt = ub2_f32_pack_weight output (Cout,taps,C0+C1) fp32, out fp32 NHWC; out = relu?(scale*acc+shift). */
-int ub2_conv_fwd_tf32(const float* in0, int ld_in0, int C0, const float* in1, int ld_in1, int C1,
-                      const float* wgt, float* out, int ld_out, int N, int H, int W, int Cout, int taps,
-                      const float* scale, const float* shift, int relu, void* stream);
-int ub2_f32_pack_weight(const float* w, float* out, int Cout, int Cin, int taps, void* stream);
-/* first conv + folded BN + ReLU: x fp32 NCHW -> out fp32 NHWC (layers.py:32-34, Cin = n_channels) */
-int ub2_f32_conv_in(const float* x, const float* w, const float* scale, const float* shift, float* out, int N,
-                    int Cin, int H, int W, int Cout, void* stream);
-int ub2_f32_maxpool(const float* in, float* out, int N, int H, int W, int C, void* stream);          /* layers.py:56 */
-int ub2_f32_upsample(const float* in, float* out, int N, int hin, int win, int hu, int wu, int Ho, int Wo, int C,
-                     void* stream);                                                              /* layers.py:78,98-102 */
-/* AttentionGate.forward after the two 1x1 projections q = W_g g (low resolution), xp = W_x x
- * (layers.py:183-192): out = x * sigmoid(BN_psi(w_psi . relu(BN_g(up q) + BN_x(xp)))) */
-int ub2_f32_gate(const float* q, const float* xp, const float* x, const float* scale_g, const float* shift_g,
-                 const float* scale_x, const float* shift_x, const float* w_psi, const float* scale_psi,
-                 const float* shift_psi, float* out, int N, int hin, int win, int H, int W, int Ci, int Cx,
-                 void* stream);
-int ub2_f32_outc(const float* a, const float* w, const float* bias, float* logits, int N, int H, int W, int C,
-                 int K, void* stream);                                                           /* layers.py:120 */
 
 /* ======================= optimizer tail ================================== */
 

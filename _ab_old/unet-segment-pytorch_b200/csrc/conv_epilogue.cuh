@@ -25,7 +25,7 @@ __device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
 
 // taddr: TMEM address of the chunk (lane quarter + column); cbase: first output channel of the
 // chunk; n_hi: end of this N tile; pix: output pixel of this thread's row (valid if `valid`).
-template <bool ACC, bool TF32 = false>
+template <bool ACC>
 __device__ __forceinline__ void epi_chunk(const ConvFwdParams& p, uint32_t taddr, int cbase, int n_hi,
                                           bool valid, size_t pix, int lane, bool want_stats,
                                           float* my_stats, float (&acc_s)[ACC ? 32 : 1],
@@ -74,22 +74,6 @@ __device__ __forceinline__ void epi_chunk(const ConvFwdParams& p, uint32_t taddr
   if (p.relu) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-  }
-  if (TF32) {
-    // fp32 activations (evaluation in TF32 mode): values rounded to TF32 where they are produced
-    float* dstf = reinterpret_cast<float*>(p.out0) + pix * p.ld0 + cbase;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (valid && cbase + g * 4 < p.Cout && cbase + g * 4 < n_hi) {
-        float4 o;
-        o.x = tf32_round(v[g * 4 + 0]);
-        o.y = tf32_round(v[g * 4 + 1]);
-        o.z = tf32_round(v[g * 4 + 2]);
-        o.w = tf32_round(v[g * 4 + 3]);
-        *reinterpret_cast<float4*>(dstf + g * 4) = o;
-      }
-    }
-    return;
   }
   uint4 held = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll

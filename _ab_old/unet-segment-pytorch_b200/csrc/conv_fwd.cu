@@ -40,7 +40,7 @@ struct FwdSmemHeader {
 // TAPS: 1 or 9 (unrolled in the producer).  ACC: BatchNorm statistics are kept as per-thread
 // running sums over all tiles of the CTA and reduced across lanes once at the end (needs one
 // 32-column chunk per epilogue warp: Cout <= 64); otherwise a register butterfly per tile.
-template <int TAPS, bool ACC, bool TF32>
+template <int TAPS, bool ACC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const ConvFwdParams p) {
@@ -92,8 +92,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // ------------------------------------------------------------ TMA producer
     // Warp-uniform control flow, one elected lane issues: keeps every operand in uniform
     // registers (a single-thread loop costs ~10x the instructions per k-step).
-    const uint32_t esz = TF32 ? 4u : 2u;
-    const uint32_t tx_bytes = 128u * kc * esz + static_cast<uint32_t>(BN) * kc * esz;
+    const uint32_t tx_bytes = 128u * kc * 2u + static_cast<uint32_t>(BN) * kc * 2u;
     const int tw = p.tiles_w, th = p.tiles_h, BW = p.BW, BH = p.BH, BI = p.BI;
     int stage = 0;
     uint32_t phase = 0;
@@ -129,15 +128,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = TF32 ? make_idesc_tf32(128, BN) : make_idesc_bf16(128, BN, 0, 0);
-    const uint32_t row_bytes = static_cast<uint32_t>(kc) * (TF32 ? 4u : 2u);   // one K chunk of a row
-    const uint32_t ltype = (row_bytes == 128) ? 2u : (row_bytes == 64) ? 4u : 6u;
-    // descriptor = {hi: SBO (8 rows of one K chunk) | version 1 | swizzle, lo: addr>>4 | LBO 1}
-    const uint32_t desc_hi = ((8u * row_bytes) >> 4) | (1u << 14) | (ltype << 29);
+    const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t ltype = (kc == 64) ? 2u : (kc == 32) ? 4u : 6u;
+    // descriptor = {hi: SBO (8 rows of kc bf16) | version 1 | swizzle, lo: addr>>4 | LBO 1}
+    const uint32_t desc_hi = ((16u * kc) >> 4) | (1u << 14) | (ltype << 29);
     const uint32_t a_lo0 = ((smem_u32(tiles) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t b_lo0 = a_lo0 + (kATileBytes >> 4);
     const uint32_t stage_inc = static_cast<uint32_t>(stage_bytes) >> 4;
-    const int kinner = static_cast<int>(row_bytes / 32);   // 32 bytes of K per MMA (16 bf16 or 8 tf32)
+    const int kinner = kc / 16;
     const int ksteps = TAPS * kchunks;
     int stage = 0;
     uint32_t phase = 0;
@@ -156,8 +154,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           for (int k = 0; k < kinner; ++k) {
             const uint64_t da = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
             const uint64_t db = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
-            if (TF32) umma_tf32(d_tmem, da, db, idesc, (ks | k) != 0);
-            else umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0);
+            umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0);
           }
           umma_commit(&hdr->empty[stage]);
           if (ks == ksteps - 1) umma_commit(&hdr->tmem_full[as]);
@@ -199,7 +196,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       mbar_wait(&hdr->tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
       for (int j = grp; j < nchunks; j += 2) {
-        epi_chunk<ACC, TF32>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn_cols + j * 32,
+        epi_chunk<ACC>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * bn_cols + j * 32,
                        n0 + j * 32, n0 + BN, valid, pix, lane, want_stats, my_stats, acc_s, acc_q);
       }
       tc_fence_before();
@@ -228,19 +225,17 @@ static int pow2_floor(int x) {
 }
 
 int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
-  if (!a.tf32) {
+  {
     // wide 3x3 layers: halo block resident in shared memory (conv_halo.cu)
     const int rc = conv_halo_launch(a, stream);
     if (rc != 1) return rc;
   }
   const int Ctot = a.C0 + a.C1;
-  const int esz = a.tf32 ? 4 : 2;
   if (a.taps != 1 && a.taps != 9) return UB2_ERR_SHAPE;
   if (a.N <= 0 || a.H <= 0 || a.W <= 0 || a.C0 <= 0 || a.C1 < 0) return UB2_ERR_SHAPE;
   if (Ctot % 16 != 0 || a.C0 % 16 != 0 || a.Cout % 16 != 0) return UB2_ERR_SHAPE;
   if (a.ld_in0 % 8 != 0 || (a.C1 > 0 && a.ld_in1 % 8 != 0) || a.ld0 % 8 != 0) return UB2_ERR_ALIGN;
-  if (a.tf32 && (a.stats != nullptr || a.accumulate || a.out1 != nullptr)) return UB2_ERR_SHAPE;  // eval only
-  int kc = 128 / esz;   // channels per 128-byte K chunk
+  int kc = 64;
   while (a.C0 % kc != 0 || Ctot % kc != 0) kc /= 2;
 
   ConvFwdParams p{};
@@ -274,7 +269,7 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   int tmem_cols = 32;
   while (tmem_cols < 2 * bn_cols) tmem_cols *= 2;
   p.tmem_cols = tmem_cols;
-  const int b_bytes = ((BN * kc * esz) + 1023) & ~1023;
+  const int b_bytes = ((BN * kc * 2) + 1023) & ~1023;
   p.stage_bytes = kATileBytes + b_bytes;
   const int stats_bytes = a.stats ? 4 * 2 * a.Cout * 4 : 0;
   const int budget = 227 * 1024 - 1024 - static_cast<int>(sizeof(FwdSmemHeader)) - stats_bytes;
@@ -287,7 +282,6 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   p.accumulate = a.accumulate;
   p.scale = a.scale; p.shift = a.shift; p.relu = a.relu;
   p.stats = a.stats;
-  p.tf32 = a.tf32;
   {
     static const int wide_env = [] { const char* e = getenv("UB2_WIDE_STORE"); return e ? atoi(e) : 1; }();
     p.wide_store = wide_env && conv_wide_store_ok(a.out0, a.ld0, a.out1, a.ld1, a.split, a.Cout);
@@ -296,16 +290,16 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   CUtensorMap tmA0, tmA1, tmB;
   const uint32_t boxA[4] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(p.BW),
                             static_cast<uint32_t>(p.BH), static_cast<uint32_t>(p.BI)};
-  int rc = make_tmap_nhwc(&tmA0, a.in0, a.N, a.H, a.W, a.C0, a.ld_in0, boxA, kc * esz, esz);
+  int rc = make_tmap_nhwc(&tmA0, a.in0, a.N, a.H, a.W, a.C0, a.ld_in0, boxA, kc * 2);
   if (rc) return rc;
   if (a.C1 > 0) {
-    rc = make_tmap_nhwc(&tmA1, a.in1, a.N, a.H, a.W, a.C1, a.ld_in1, boxA, kc * esz, esz);
+    rc = make_tmap_nhwc(&tmA1, a.in1, a.N, a.H, a.W, a.C1, a.ld_in1, boxA, kc * 2);
     if (rc) return rc;
   } else {
     tmA1 = tmA0;
   }
   rc = make_tmap_2d(&tmB, a.wgt, static_cast<uint64_t>(a.taps) * Ctot, a.Cout,
-                    static_cast<uint64_t>(a.taps) * Ctot, kc, BN, kc * esz, esz);
+                    static_cast<uint64_t>(a.taps) * Ctot, kc, BN, kc * 2);
   if (rc) return rc;
 
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
@@ -320,26 +314,21 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
     cudaError_t e = cudaSuccess;
     const int lim = 227 * 1024;
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<9, true, false>, attr, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<9, false, false>, attr, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<1, true, false>, attr, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<1, false, false>, attr, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<9, false, true>, attr, lim);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<1, false, true>, attr, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<9, true>, attr, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<9, false>, attr, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<1, true>, attr, lim);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_fwd_kernel<1, false>, attr, lim);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   // running-sum statistics need one 32-column chunk per epilogue warp and a single N tile
   const bool acc = a.stats != nullptr && bn_cols <= 64 && p.n_tiles == 1;
-  if (a.tf32) {
-    if (a.taps == 9) conv_fwd_kernel<9, false, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
-    else conv_fwd_kernel<1, false, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
-  } else if (a.taps == 9) {
-    if (acc) conv_fwd_kernel<9, true, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
-    else conv_fwd_kernel<9, false, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+  if (a.taps == 9) {
+    if (acc) conv_fwd_kernel<9, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+    else conv_fwd_kernel<9, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
   } else {
-    if (acc) conv_fwd_kernel<1, true, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
-    else conv_fwd_kernel<1, false, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+    if (acc) conv_fwd_kernel<1, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+    else conv_fwd_kernel<1, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -98,72 +98,21 @@ __global__ void seg_stats_finalize_kernel(const double* __restrict__ partials, i
   stats[(static_cast<size_t>(n) * 4 + k) * C + c] = static_cast<float>(s[0]);
 }
 
-// DiceBCELoss (unet/utils/loss.py:153-191) from the statistics table, value and gradient table in
-// one tiny launch instead of ~40 O(N*C) tensor expressions and their autograd:
-//   bce  = (1/N) sum_n [ ce[n,0] (1-cw)/(cnt[n,0]+s_ce) + ce[n,1] cw/(cnt[n,1]+s_ce) ]   (loss.py:134-148)
-//   dice = (2 I + s_d) / (P + cnt + s_d),  loss_dice = 1 - mean over n and c >= c0 of dice   (loss.py:70-85)
-//   loss = ce_weight * bce + dice_weight * loss_dice                                         (loss.py:184-191)
-// stats (N,4,C) = {cnt, ce, I, P}; coef (N,3,C) = {dL/dce, dL/dI, dL/dP}.  One block, fixed order.
-__global__ void __launch_bounds__(256)
-dice_bce_head_kernel(const float* __restrict__ stats, int N, int C, float ce_weight, float dice_weight,
-                     float class_weight, float ce_smooth, float dice_smooth, int ignore_background,
-                     float* __restrict__ loss, float* __restrict__ coef) {
-  __shared__ double s_bce[256], s_dice[256];
-  const int c0 = (ignore_background && C > 1) ? 1 : 0;
-  const float inv_n = 1.f / static_cast<float>(N);
-  const float inv_d = 1.f / static_cast<float>(N * (C - c0));
-  double bce = 0.0, dice = 0.0;
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    const float* st = stats + static_cast<size_t>(n) * 4 * C;
-    float* cf = coef + static_cast<size_t>(n) * 3 * C;
-    for (int c = 0; c < C; ++c) {
-      const float cnt = st[c], ce = st[C + c], inter = st[2 * C + c], psum = st[3 * C + c];
-      float dce = 0.f, dI = 0.f, dP = 0.f;
-      if (c < 2) {   // the balanced CE weights classes 0 and 1 only (binary masks, loss.py:139-145)
-        const float wgt = (c == 0 ? 1.f - class_weight : class_weight) / (cnt + ce_smooth);
-        bce += static_cast<double>(ce * wgt);
-        dce = ce_weight * wgt * inv_n;
-      }
-      if (c >= c0) {
-        const float den = psum + cnt + dice_smooth;
-        const float d = (2.f * inter + dice_smooth) / den;
-        dice += static_cast<double>(d);
-        dI = -dice_weight * inv_d * 2.f / den;
-        dP = dice_weight * inv_d * d / den;
-      }
-      cf[c] = dce;
-      cf[C + c] = dI;
-      cf[2 * C + c] = dP;
-    }
-  }
-  s_bce[threadIdx.x] = bce;
-  s_dice[threadIdx.x] = dice;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double b = 0.0, d = 0.0;
-    for (int i = 0; i < 256; ++i) { b += s_bce[i]; d += s_dice[i]; }
-    loss[0] = static_cast<float>(ce_weight * (b * inv_n) + dice_weight * (1.0 - d * inv_d));
-  }
-}
-
-// coef[n][3][C] = {dce, dI, dP}; gscale (optional, one float) = the upstream gradient of the loss
+// coef[n][3][C] = {dce, dI, dP} (already multiplied by the upstream gradient on the host side)
 template <int C>
 __global__ void __launch_bounds__(kLossThreads)
 seg_stats_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ targets,
-                     const float* __restrict__ coef, const float* __restrict__ gscale, long long HW,
-                     float* __restrict__ dlogits) {
+                     const float* __restrict__ coef, long long HW, float* __restrict__ dlogits) {
   const int n = blockIdx.y;
   const float* z = logits + static_cast<size_t>(n) * C * HW;
   const long long* t = targets + static_cast<size_t>(n) * HW;
   float* dz = dlogits + static_cast<size_t>(n) * C * HW;
   float dce[C], dI[C], dP[C];
 #pragma unroll
-  const float gs = gscale != nullptr ? __ldg(gscale) : 1.f;
-#pragma unroll
   for (int c = 0; c < C; ++c) {
-    dce[c] = gs * __ldg(coef + (static_cast<size_t>(n) * 3 + 0) * C + c);
-    dI[c] = gs * __ldg(coef + (static_cast<size_t>(n) * 3 + 1) * C + c);
-    dP[c] = gs * __ldg(coef + (static_cast<size_t>(n) * 3 + 2) * C + c);
+    dce[c] = __ldg(coef + (static_cast<size_t>(n) * 3 + 0) * C + c);
+    dI[c] = __ldg(coef + (static_cast<size_t>(n) * 3 + 1) * C + c);
+    dP[c] = __ldg(coef + (static_cast<size_t>(n) * 3 + 2) * C + c);
   }
   for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < HW;
        r += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -195,9 +144,9 @@ static int launch_stats(const float* logits, const long long* targets, int N, lo
   return static_cast<int>(cudaGetLastError());
 }
 template <int C>
-static int launch_bwd(const float* logits, const long long* targets, const float* coef, const float* gscale,
-                      int N, long long HW, float* dlogits, int blocks, cudaStream_t s) {
-  seg_stats_bwd_kernel<C><<<dim3(blocks, N), kLossThreads, 0, s>>>(logits, targets, coef, gscale, HW, dlogits);
+static int launch_bwd(const float* logits, const long long* targets, const float* coef, int N,
+                      long long HW, float* dlogits, int blocks, cudaStream_t s) {
+  seg_stats_bwd_kernel<C><<<dim3(blocks, N), kLossThreads, 0, s>>>(logits, targets, coef, HW, dlogits);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -233,29 +182,20 @@ int ub2_seg_stats(const float* logits, const long long* targets, int N, int C, l
   }
 }
 
-int ub2_dice_bce_head(const float* stats, int N, int C, float ce_weight, float dice_weight, float class_weight,
-                      float ce_smooth, float dice_smooth, int ignore_background, float* loss, float* coef,
-                      void* stream) {
-  if (N <= 0 || C < 1 || C > kLossMaxC) return UB2_ERR_SHAPE;
-  dice_bce_head_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, N, C, ce_weight, dice_weight, class_weight, ce_smooth, dice_smooth, ignore_background, loss, coef);
-  return static_cast<int>(cudaGetLastError());
-}
-
-int ub2_seg_stats_bwd(const float* logits, const long long* targets, const float* coef, const float* gscale,
-                      int N, int C, long long HW, float* dlogits, void* stream) {
+int ub2_seg_stats_bwd(const float* logits, const long long* targets, const float* coef, int N, int C,
+                      long long HW, float* dlogits, void* stream) {
   if (N <= 0 || HW <= 0 || C < 1 || C > kLossMaxC) return UB2_ERR_SHAPE;
   const int blocks = loss_blocks(N, HW);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (C) {
-    case 1: return launch_bwd<1>(logits, targets, coef, gscale, N, HW, dlogits, blocks, s);
-    case 2: return launch_bwd<2>(logits, targets, coef, gscale, N, HW, dlogits, blocks, s);
-    case 3: return launch_bwd<3>(logits, targets, coef, gscale, N, HW, dlogits, blocks, s);
-    case 4: return launch_bwd<4>(logits, targets, coef, gscale, N, HW, dlogits, blocks, s);
-    case 5: return launch_bwd<5>(logits, targets, coef, gscale, N, HW, dlogits, blocks, s);
-    case 6: return launch_bwd<6>(logits, targets, coef, gscale, N, HW, dlogits, blocks, s);
-    case 7: return launch_bwd<7>(logits, targets, coef, gscale, N, HW, dlogits, blocks, s);
-    default: return launch_bwd<8>(logits, targets, coef, gscale, N, HW, dlogits, blocks, s);
+    case 1: return launch_bwd<1>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 2: return launch_bwd<2>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 3: return launch_bwd<3>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 4: return launch_bwd<4>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 5: return launch_bwd<5>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 6: return launch_bwd<6>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    case 7: return launch_bwd<7>(logits, targets, coef, N, HW, dlogits, blocks, s);
+    default: return launch_bwd<8>(logits, targets, coef, N, HW, dlogits, blocks, s);
   }
 }
 

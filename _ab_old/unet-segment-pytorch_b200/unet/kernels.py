@@ -436,27 +436,15 @@ def seg_stats(logits, targets):
     return stats
 
 
-def seg_stats_bwd(logits, targets, coef, gscale=None):
-    """coef (N,3,C) fp32 = {dL/dCE, dL/dI, dL/dP} (times the device scalar ``gscale`` if given);
-    returns dL/dlogits (N,C,H,W) fp32."""
+def seg_stats_bwd(logits, targets, coef):
+    """coef (N,3,C) fp32 = {dL/dCE, dL/dI, dL/dP}; returns dL/dlogits (N,C,H,W) fp32."""
     n, c, h, w = logits.shape
     coef = coef.contiguous()
     assert coef.dtype == F32 and coef.shape == (n, 3, c)
-    assert gscale is None or (gscale.dtype == F32 and gscale.numel() == 1)
     dl = torch.empty_like(logits)
-    _C.call("ub2_seg_stats_bwd", ptr(logits), ptr(targets.contiguous()), ptr(coef), ptr(gscale), n, c,
+    _C.call("ub2_seg_stats_bwd", ptr(logits), ptr(targets.contiguous()), ptr(coef), n, c,
             c_longlong(h * w), ptr(dl), stream())
     return dl
-
-
-def dice_bce_head(stats, ce_weight, dice_weight, class_weight, ce_smooth, dice_smooth, ignore_background):
-    """stats (N,4,C) -> (loss 0-dim fp32, coef (N,3,C) fp32)."""
-    n, _, c = stats.shape
-    loss = torch.empty((1,), device=stats.device, dtype=F32)
-    coef = torch.empty((n, 3, c), device=stats.device, dtype=F32)
-    _C.call("ub2_dice_bce_head", ptr(stats), n, c, c_float(ce_weight), c_float(dice_weight), c_float(class_weight),
-            c_float(ce_smooth), c_float(dice_smooth), int(ignore_background), ptr(loss), ptr(coef), stream())
-    return loss[0], coef
 
 
 def confusion(pred, target, num_classes, cm, ignore_index=None, threshold=None, mask_out=None):

@@ -369,26 +369,6 @@ class SegStats(torch.autograd.Function):
         return K.seg_stats_bwd(logits, targets, coef), None
 
 
-class DiceBCEFn(torch.autograd.Function):
-    """DiceBCELoss (loss.py:153-191) end to end: statistics pass, one head launch for the value and
-    the gradient table, one backward pass over the pixels."""
-
-    @staticmethod
-    def forward(ctx, logits, targets, ce_weight, dice_weight, class_weight, ce_smooth, dice_smooth, ignore_bg):
-        if not logits.is_cuda:
-            raise RuntimeError("unet-b200 losses run on CUDA tensors only (no CPU fallback)")
-        logits = logits.contiguous().float()
-        loss, coef = K.dice_bce_head(K.seg_stats(logits, targets), ce_weight, dice_weight, class_weight,
-                                     ce_smooth, dice_smooth, ignore_bg)
-        ctx.save_for_backward(logits, targets, coef)
-        return loss
-
-    @staticmethod
-    def backward(ctx, gout):
-        logits, targets, coef = ctx.saved_tensors
-        return (K.seg_stats_bwd(logits, targets, coef, gscale=gout.contiguous().float()),) + (None,) * 7
-
-
 class MaxPool2x2(torch.autograd.Function):
     """Standalone nn.MaxPool2d(2) (layers.py:56) for `Down` used outside the fused network."""
 

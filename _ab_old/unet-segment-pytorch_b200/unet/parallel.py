@@ -1,0 +1,256 @@
+"""Batch-sharded data-parallel training step — the B200 form of the reference's
+gradient-accumulation loop (scripts/train.py:103-161).
+
+The reference reaches its effective batch by running ``accumulation_steps`` micro-batches one
+after another on one device: each micro-batch has its own BatchNorm batch statistics, its loss
+is divided by ``accumulation_steps`` (train.py:133), gradients sum into ``.grad`` and one
+clip + optimizer step follows (train.py:139-143).  Here the micro-batches run at the same time,
+one per GPU (one process per GPU): rank r computes forward/backward on its shard with the loss
+divided by ``world_size``, gradients are summed with NCCL all-reduce over NVLink, and every
+rank then applies the identical clip + optimizer step.  Up to summation order this is the same
+arithmetic (no SyncBN: statistics stay per micro-batch, exactly as in the reference).
+
+Gradients live in a few flat fp32 buckets cut in backward order; a bucket's all-reduce is
+launched from an autograd hook as soon as its last gradient has been accumulated, on NCCL's
+own stream, so communication overlaps the rest of backward.  With ``world_size == 1`` the same
+code runs without collectives.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .optim import FusedAdamW
+
+
+class _Bucket:
+    __slots__ = ("flat", "params", "pending", "work", "deferred")
+
+    def __init__(self, flat, params):
+        self.flat, self.params, self.pending, self.work = flat, params, 0, None
+        self.deferred = []   # split-K folds of this bucket's conv weights, launched together
+
+
+class _GradSink:
+    """What unet.ops talks to during the trainer's backward pass (see ops.GRAD_SINK)."""
+
+    def __init__(self, trainer):
+        self.trainer = trainer
+
+    def __call__(self, param):
+        self.trainer._grad_sink(param)
+
+    def defer_reduce(self, param, item):
+        self.trainer._defer_reduce(param, item)
+
+
+class BatchShardedTrainer:
+    """fwd + loss/world + bwd (+ overlapped gradient all-reduce) + clip + optimizer step.
+
+    Parameters
+    ----------
+    model, criterion, optimizer : as built by the reference's train.py (:306-350)
+    grad_clip : max gradient norm (train.py:141), 0 disables
+    bucket_mb : flat gradient bucket size
+    process_group : None -> default group if torch.distributed is initialised
+    """
+
+    def __init__(self, model, criterion, optimizer, grad_clip: float = 0.0, bucket_mb: float = 24.0,
+                 process_group=None, cuda_graph: bool = False, graph_warmup: int = 3):
+        self.model, self.criterion, self.optimizer, self.grad_clip = model, criterion, optimizer, grad_clip
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.buckets: List[_Bucket] = []
+        self._bucket_of = {}
+        self._build_buckets(bucket_mb)
+        self._steps = 0
+        self._packer = None   # all bf16 weight packs of the model, rebuilt by one launch per step
+        # CUDA-graph replay of the whole step: a 512^2 batch-4 step is ~800 kernel launches, more
+        # host time than GPU time when issued one by one.  Every kernel of the path is
+        # stream-ordered with no host synchronisation, so the step is captured once per input
+        # shape (after `graph_warmup` eager steps) and replayed.
+        self.cuda_graph = cuda_graph
+        self.graph_warmup = graph_warmup
+        self._graphs = {}
+        self._eager_steps = {}
+
+    # ------------------------------------------------------------------ flat gradient buckets
+    def _build_buckets(self, bucket_mb: float) -> None:
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        limit = int(bucket_mb * (1 << 20) / 4)
+        groups, cur, cur_n = [], [], 0
+        for p in reversed(params):  # backward produces gradients roughly in reverse registration order
+            cur.append(p)
+            cur_n += p.numel()
+            if cur_n >= limit:
+                groups.append(cur)
+                cur, cur_n = [], 0
+        if cur:
+            groups.append(cur)
+        pad = lambda n: (n + 31) & ~31   # every view starts on a 128-byte boundary (vector access)
+        for g in groups:
+            flat = torch.zeros(sum(pad(p.numel()) for p in g), device=g[0].device, dtype=torch.float32)
+            off = 0
+            for p in g:
+                p.grad = flat[off:off + p.numel()].view_as(p)  # autograd accumulates in place into the view
+                off += pad(p.numel())
+            b = _Bucket(flat, g)
+            self.buckets.append(b)
+            for p in g:
+                self._bucket_of[id(p)] = b
+                if self.world > 1:
+                    p.register_post_accumulate_grad_hook(self._make_hook(b))
+
+    def _bucket_ready(self, bucket: _Bucket, n: int = 1) -> None:
+        bucket.pending -= n
+        if bucket.deferred and bucket.pending == len(bucket.deferred):
+            # every other gradient of the bucket is in: fold all its split-K partials in one go
+            from .kernels import wgrad_reduce_multi
+            items, bucket.deferred = bucket.deferred, []
+            wgrad_reduce_multi(items, accumulate=True)
+            bucket.pending -= len(items)
+        if bucket.pending == 0 and self.world > 1 and bucket.work is None:
+            bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _defer_reduce(self, param, item) -> None:
+        b = self._bucket_of.get(id(param))
+        if b is None:   # not one of ours: fold it now
+            from .kernels import wgrad_reduce
+            wgrad_reduce(*item, accumulate=True)
+            return
+        b.deferred.append(item)
+        self._bucket_ready(b, 0)
+
+    def _flush_deferred(self) -> None:
+        """End of backward: buckets in which some parameter received no gradient this step."""
+        from .kernels import wgrad_reduce_multi
+        for b in self.buckets:
+            if b.deferred:
+                items, b.deferred = b.deferred, []
+                wgrad_reduce_multi(items, accumulate=True)
+                b.pending -= len(items)
+
+    def _make_hook(self, bucket: _Bucket):
+        return lambda _param: self._bucket_ready(bucket)
+
+    def _grad_sink(self, param) -> None:
+        """Called by unet.ops when a kernel has accumulated ``param``'s gradient straight into its
+        bucket view (no autograd AccumulateGrad node runs for it, hence no hook)."""
+        b = self._bucket_of.get(id(param))
+        if b is not None:
+            self._bucket_ready(b)
+
+    # ------------------------------------------------------------------ one optimizer step
+    def _step_body(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        self.model.train()
+        for b in self.buckets:
+            b.flat.zero_()
+            b.pending = len(b.params)
+            b.work = None
+            b.deferred = []
+        dev = next(self.model.parameters()).device
+        if dev.type == "cuda":
+            if self._packer is None:
+                from .kernels import WeightPacker
+                self._packer = WeightPacker([m.weight for m in self.model.modules()
+                                             if isinstance(m, torch.nn.Conv2d) and m.weight.is_cuda])
+            self._packer.run()
+        prev_sink, prev_packs = ops.GRAD_SINK, ops.PACKS
+        ops.GRAD_SINK, ops.PACKS = _GradSink(self), self._packer
+        try:
+            outputs = self.model(images)
+            loss = self.criterion(outputs, masks)
+            (loss / self.world).backward()
+            self._flush_deferred()
+        finally:
+            ops.GRAD_SINK, ops.PACKS = prev_sink, prev_packs
+        if self.world > 1:
+            for b in self.buckets:
+                if b.work is None:  # a parameter without gradient this step
+                    b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            for b in self.buckets:
+                b.work.wait()
+        if isinstance(self.optimizer, FusedAdamW):
+            # clip + AdamW in two multi-tensor launches (csrc/optim.cu)
+            self.optimizer.max_grad_norm = float(self.grad_clip)
+            self.optimizer.step()
+        else:
+            if self.grad_clip > 0:
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip, foreach=True)
+            self.optimizer.step()
+        return loss.detach()
+
+    def _optimizer_capturable(self) -> bool:
+        if isinstance(self.optimizer, FusedAdamW):
+            return True
+        return all(g.get("capturable", False) for g in self.optimizer.param_groups)
+
+    def step(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        """One micro-batch per rank and one optimizer step.  ``images`` / ``masks`` may be host
+        (pinned) tensors: they are copied to this rank's GPU asynchronously.  Returns the
+        un-divided micro-batch loss as a 0-dim device tensor (no host sync)."""
+        dev = next(self.model.parameters()).device
+        self._steps += 1
+        use_graph = self.cuda_graph and dev.type == "cuda" and self._optimizer_capturable()
+        if not use_graph:
+            return self._step_body(images.to(dev, non_blocking=True), masks.to(dev, non_blocking=True))
+        key = (tuple(images.shape), images.dtype, tuple(masks.shape), masks.dtype)
+        entry = self._graphs.get(key)
+        if entry is None:
+            done = self._eager_steps.get(key, 0)
+            if done < self.graph_warmup:
+                # eager warm-up (lazy initialisation, allocator, NCCL) on a side stream, as
+                # torch.cuda.graph requires
+                self._eager_steps[key] = done + 1
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    loss = self._step_body(images.to(dev, non_blocking=True), masks.to(dev, non_blocking=True))
+                torch.cuda.current_stream(dev).wait_stream(side)
+                return loss
+            gx = torch.empty(images.shape, dtype=images.dtype, device=dev)
+            gt = torch.empty(masks.shape, dtype=masks.dtype, device=dev)
+            gx.copy_(images, non_blocking=True)
+            gt.copy_(masks, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                gloss = self._step_body(gx, gt)
+            entry = self._graphs[key] = (graph, gx, gt, gloss)
+            # the capture itself does not execute: fall through and replay it for this step
+        graph, gx, gt, gloss = entry
+        gx.copy_(images, non_blocking=True)
+        gt.copy_(masks, non_blocking=True)
+        if isinstance(self.optimizer, FusedAdamW):
+            self.optimizer.sync_hyperparams()   # a scheduler may have changed the learning rate
+        graph.replay()
+        return gloss
+
+    def release_graphs(self) -> None:
+        """Drop the captured step graphs (they hold references to NCCL work and pool memory)."""
+        self._graphs.clear()
+        self._eager_steps.clear()
+
+    @torch.no_grad()
+    def evaluate(self, images: torch.Tensor, masks: torch.Tensor, metrics=None) -> torch.Tensor:
+        """validate() of the reference (train.py:164-197) for one batch: eval-mode forward
+        (BatchNorm folded, ReLU fused), loss, and device-side confusion-matrix update."""
+        dev = next(self.model.parameters()).device
+        images = images.to(dev, non_blocking=True)
+        masks = masks.to(dev, non_blocking=True)
+        self.model.eval()
+        out = self.model(images)
+        if metrics is not None:
+            metrics.update(out, masks)
+        return self.criterion(out, masks)
+
+    def all_reduce_confusion(self, metrics) -> None:
+        """Confusion matrices are additive over shards: sum them across ranks."""
+        if self.world == 1:
+            return
+        cm = torch.from_numpy(metrics.confusion_matrix.copy()).to(next(self.model.parameters()).device)
+        dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=self.group)
+        metrics.confusion_matrix = cm.cpu().numpy()

@@ -83,14 +83,9 @@ class DiceBCELoss(nn.Module):
         self.dice_loss = DiceLoss(ignore_background=True)
 
     def forward(self, predictions: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
-        d = self.dice_loss
-        if d.reduction == 'mean' and predictions.dim() == 4:
-            # value and gradient table in one launch (csrc/loss.cu: dice_bce_head_kernel)
-            return ops.DiceBCEFn.apply(predictions, targets, float(self.ce_weight), float(self.dice_weight),
-                                       float(self.balanced_ce.class_weight), float(self.balanced_ce.smooth),
-                                       float(d.smooth), bool(d.ignore_background))
         cnt, ce, inter, psum = _stats(predictions, targets)
         bce = _balanced_ce_from_stats(cnt, ce, self.balanced_ce.class_weight, self.balanced_ce.smooth)
+        d = self.dice_loss
         dice = _dice_from_stats(cnt, inter, psum, d.smooth, d.reduction, d.ignore_background)
         return self.ce_weight * bce + self.dice_weight * dice
 
