@@ -321,3 +321,27 @@ def test_direct_gradient_sink_equals_autograd():
         ops.GRAD_SINK = None
     for p, r in zip(params, ref):
         assert torch.allclose(p.grad, 2 * r, rtol=1e-5, atol=1e-6)
+
+
+def test_inference_engine_graph_equals_eager():
+    """InferenceEngine (weight packs built once, forward replayed as a CUDA graph) == model.eval()(x)."""
+    from unet.inference import InferenceEngine
+    from unet.models import AttentionUNet
+    torch.manual_seed(4)
+    model = AttentionUNet(1, 2, True, 32).cuda().eval()
+    engine = InferenceEngine(model)
+    for n in (1, 2):
+        x, _ = O.synthetic_batch(n, 64, 64, seed=20 + n)
+        with torch.no_grad():
+            ref = model(x.cuda())
+        outs = [engine(x.pin_memory()).clone() for _ in range(4)]   # eager warm-ups, capture, replays
+        for o in outs:
+            assert torch.equal(o, ref)
+    with torch.no_grad():   # new weights: refresh() rebuilds the packs and drops the graphs
+        for p in model.parameters():
+            p.mul_(1.01)
+    engine.refresh()
+    x, _ = O.synthetic_batch(1, 64, 64, seed=30)
+    with torch.no_grad():
+        ref = model(x.cuda())
+    assert torch.equal(engine(x).clone(), ref)

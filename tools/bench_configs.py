@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "unet-segment-pytorch_b200"))
 sys.path.insert(0, ROOT)
 from oracle import unet_oracle as O  # noqa: E402  (synthetic inputs only)
+from unet.inference import InferenceEngine  # noqa: E402
 from unet.models import AttentionUNet, UNet  # noqa: E402
 from unet.optim import FusedAdamW  # noqa: E402
 from unet.parallel import BatchShardedTrainer  # noqa: E402
@@ -57,11 +58,11 @@ if "cfg5" in which:
         x = x.repeat(reps, 1, 1, 1)[:b].to(dev)
         t = t.repeat(reps, 1, 1)[:b].to(dev)
 
-        def step():
-            with torch.no_grad():
-                logits = model(x)
-                metrics.update(logits, t)
+        engine = InferenceEngine(model)
 
-        ms = timed(step, 5 if b >= 64 else 20, 3)
+        def step():
+            metrics.update(engine(x), t)
+
+        ms = timed(step, 5 if b >= 64 else 20, 4)
         print(f"cfg5 AttentionUNet eval batch {b:3d}: {ms:8.2f} ms, {b / ms * 1e3:7.1f} img/s, "
               f"{b * 327_891_812_352 / ms / 1e9:6.0f} TFLOP/s, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
