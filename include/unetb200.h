@@ -257,6 +257,10 @@ int ub2_grad_sumsq(const long long* ptrs, const long long* numel, const int* chu
 int ub2_adamw_step(const long long* ptrs, const long long* numel, const int* group, const int* chunks,
                    int nchunks, int T, const double* partial, const float* hyper, const float* step,
                    float* total_norm, int write_grads, void* stream);
+/* ModelEMA.update (unet/utils/general.py:155-184) for all parameters and buffers in one launch:
+ * desc (T,4) int64 = {dst, src, numel, kind (0: dst = decay*dst + (1-decay)*src fp32; 1: copy fp32;
+ * 2: copy int64)}; chunks (nchunks,2) int32 as for ub2_adamw_step; *decay fp32 in device memory. */
+int ub2_ema_update(const long long* desc, const int* chunks, int nchunks, const float* decay, void* stream);
 
 #ifdef __cplusplus
 }

@@ -148,6 +148,50 @@ adamw_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ n
   }
 }
 
+// ModelEMA.update (unet/utils/general.py:155-184) as one multi-tensor launch: parameters
+// ema = decay*ema + (1-decay)*p, buffers copied (fp32 running statistics, int64 counters).
+// desc (T,4) int64 = {dst, src, numel, kind: 0 lerp fp32, 1 copy fp32, 2 copy int64}; decay from
+// device memory (graph-capturable while the host ramps it up during warm-up).
+__global__ void __launch_bounds__(kOptThreads)
+ema_update_kernel(const long long* __restrict__ desc, const int2* __restrict__ chunks, int chunk_elems,
+                  const float* __restrict__ decay_ptr) {
+  const int2 ch = chunks[blockIdx.x];
+  const long long* d = desc + 4 * ch.x;
+  const long long n = d[2];
+  const long long begin = ch.y;
+  const long long end = (begin + chunk_elems < n) ? begin + chunk_elems : n;
+  const int kind = static_cast<int>(d[3]);
+  if (kind == 2) {
+    long long* dst = reinterpret_cast<long long*>(d[0]);
+    const long long* src = reinterpret_cast<const long long*>(d[1]);
+    for (long long i = begin + threadIdx.x; i < end; i += kOptThreads) dst[i] = src[i];
+    return;
+  }
+  float* dst = reinterpret_cast<float*>(d[0]);
+  const float* src = reinterpret_cast<const float*>(d[1]);
+  if (kind == 1) {
+    for (long long i = begin + threadIdx.x; i < end; i += kOptThreads) dst[i] = src[i];
+    return;
+  }
+  const float decay = __ldg(decay_ptr);
+  const float alpha = 1.f - decay;
+  long long vend = begin;
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+    vend = begin + ((end - begin) & ~3LL);
+    for (long long i = begin + threadIdx.x * 4LL; i < vend; i += kOptThreads * 4LL) {
+      float4 e = *reinterpret_cast<float4*>(dst + i);
+      const float4 p = *reinterpret_cast<const float4*>(src + i);
+      // mul_(decay).add_(p, alpha = 1 - decay): two roundings, as ATen
+      e.x = e.x * decay + alpha * p.x;
+      e.y = e.y * decay + alpha * p.y;
+      e.z = e.z * decay + alpha * p.z;
+      e.w = e.w * decay + alpha * p.w;
+      *reinterpret_cast<float4*>(dst + i) = e;
+    }
+  }
+  for (long long i = vend + threadIdx.x; i < end; i += kOptThreads) dst[i] = dst[i] * decay + alpha * src[i];
+}
+
 }  // namespace ub2
 
 using namespace ub2;
@@ -171,6 +215,13 @@ int ub2_adamw_step(const long long* ptrs, const long long* numel, const int* gro
   adamw_kernel<<<nchunks, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       ptrs, numel, group, reinterpret_cast<const int2*>(chunks), nchunks, ub2_adamw_chunk_elems(), T, partial,
       hyper, step, total_norm, write_grads);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_ema_update(const long long* desc, const int* chunks, int nchunks, const float* decay, void* stream) {
+  if (nchunks <= 0) return UB2_ERR_SHAPE;
+  ema_update_kernel<<<nchunks, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      desc, reinterpret_cast<const int2*>(chunks), ub2_adamw_chunk_elems(), decay);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -59,7 +59,7 @@ class BatchShardedTrainer:
     """
 
     def __init__(self, model, criterion, optimizer, grad_clip: float = 0.0, bucket_mb: float = 24.0,
-                 process_group=None, cuda_graph: bool = False, graph_warmup: int = 3):
+                 process_group=None, cuda_graph: bool = False, graph_warmup: int = 3, ema=None):
         self.model, self.criterion, self.optimizer, self.grad_clip = model, criterion, optimizer, grad_clip
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
@@ -67,6 +67,9 @@ class BatchShardedTrainer:
         self._bucket_of = {}
         self._build_buckets(bucket_mb)
         self._steps = 0
+        # unet.utils.general.ModelEMA (or None): updated after every optimizer step like the
+        # reference's loop does (scripts/train.py:146-147), as one launch inside the step graph
+        self.ema = ema
         self._packer = None   # all bf16 weight packs of the model, rebuilt by one launch per step
         # CUDA-graph replay of the whole step: a 512^2 batch-4 step is ~800 kernel launches, more
         # host time than GPU time when issued one by one.  Every kernel of the path is
@@ -181,6 +184,8 @@ class BatchShardedTrainer:
             if self.grad_clip > 0:
                 torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.grad_clip, foreach=True)
             self.optimizer.step()
+        if self.ema is not None:
+            self.ema.update(self.model, _advance=False)
         return loss.detach()
 
     def _optimizer_capturable(self) -> bool:
@@ -194,6 +199,8 @@ class BatchShardedTrainer:
         un-divided micro-batch loss as a 0-dim device tensor (no host sync)."""
         dev = next(self.model.parameters()).device
         self._steps += 1
+        if self.ema is not None:
+            self.ema.prepare(self.model)   # host side: counter, warm-up decay -> device memory
         use_graph = self.cuda_graph and dev.type == "cuda" and self._optimizer_capturable()
         if not use_graph:
             return self._step_body(images.to(dev, non_blocking=True), masks.to(dev, non_blocking=True))

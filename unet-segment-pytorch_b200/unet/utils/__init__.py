@@ -1,7 +1,8 @@
-"""Loss and metrics of the hot path (the reference's general/callbacks/plots utilities are
-orchestration and are used unchanged from the reference)."""
+"""Loss, metrics and the EMA update of the hot path (the rest of the reference's general / callbacks /
+plots utilities is orchestration and is used unchanged from the reference)."""
+from .general import ModelEMA
 from .loss import BalancedCELoss, DeepSupervisionLoss, DiceBCELoss, DiceLoss, create_loss_function
 from .metrics import SegmentationMetrics, compute_dice, compute_iou
 
 __all__ = ["DiceLoss", "BalancedCELoss", "DiceBCELoss", "DeepSupervisionLoss", "create_loss_function",
-           "SegmentationMetrics", "compute_iou", "compute_dice"]
+           "SegmentationMetrics", "compute_iou", "compute_dice", "ModelEMA"]
