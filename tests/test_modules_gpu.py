@@ -345,3 +345,63 @@ def test_inference_engine_graph_equals_eager():
     with torch.no_grad():
         ref = model(x.cuda())
     assert torch.equal(engine(x).clone(), ref)
+
+
+def test_deep_supervision_outputs_and_loss():
+    """deep_supervision=True in training mode returns [main, ds1, ds2, ds3] at the input size
+    (unet.py:204-211); DeepSupervisionLoss (loss.py:194-229) of them matches the oracle's; in eval
+    mode a single tensor comes back."""
+    from unet.utils.loss import DeepSupervisionLoss, DiceBCELoss
+    model, sd, cfg = _build(True, 32, 31, deep_supervision=True)
+    x, t = O.synthetic_batch(2, 64, 64, seed=7, fg_fraction=0.05)
+    model = model.cuda().train()
+    outs = model(x.cuda())
+    assert isinstance(outs, list) and len(outs) == 4 and all(o.shape == (2, 2, 64, 64) for o in outs)
+    loss = DeepSupervisionLoss(DiceBCELoss())(outs, t.cuda())
+    ref = O.deep_supervision_loss([o.detach().cpu().float() for o in outs], t)
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 1e-6
+    loss.backward()
+    heads = [p for n, p in model.named_parameters() if n.startswith("ds_out")]
+    assert len(heads) == 6 and all(p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0
+                                   for p in heads)
+    ref_outs = O.unet_forward(x, O.clone_state(sd), attention=True, deep_supervision=True, training=True)
+    for o, r in zip(outs, ref_outs):   # train mode at random init: loose gate (SURVEY App. C)
+        assert rel_l2(o, r) < 0.5
+    model.eval()
+    with torch.no_grad():
+        assert torch.is_tensor(model(x.cuda()))
+
+
+def test_eval_end_to_end_transposed_conv_variant():
+    """bilinear=False (ConvTranspose2d up-sampling, layers.py:81, :217-221), eval mode."""
+    model, sd, cfg = _build(True, 32, 33, bilinear=False)
+    x, _ = O.synthetic_batch(2, 64, 64, seed=8)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        logits = model(x.cuda())
+    ref = O.unet_forward(x, sd, attention=True, bilinear=False, training=False)
+    assert rel_l2(logits, ref) <= 2e-2, f"eval logits rel-L2 {rel_l2(logits, ref):.3e}"
+
+
+def test_full_size_step_is_deterministic_and_finite():
+    """BASELINE configs[1] size (4 x 1 x 512 x 512, base 64): two identical training steps from the
+    same state give bit-identical losses and gradients (fixed-order reductions, no atomics), and the
+    batch-statistics identity holds: the raw conv outputs feeding every BatchNorm are normalised to
+    zero mean / unit variance, so the BN running means move by exactly momentum * batch mean."""
+    from unet.models import AttentionUNet
+    from unet.utils.loss import DiceBCELoss
+    x, t = O.synthetic_batch(4, 512, 512, seed=1234)
+    x, t = x.cuda(), t.cuda()
+    runs = []
+    for _ in range(2):
+        torch.manual_seed(42)
+        model = AttentionUNet(1, 2, True, 64).cuda().train()
+        loss = DiceBCELoss()(model(x), t)
+        loss.backward()
+        runs.append((loss.item(), [p.grad.clone() for p in model.parameters()],
+                     model.inc.double_conv[1].running_mean.clone()))
+    (l0, g0, rm0), (l1, g1, rm1) = runs
+    assert l0 == l1 and torch.isfinite(torch.tensor(l0))
+    for a, b in zip(g0, g1):
+        assert torch.equal(a, b) and torch.isfinite(a).all()
+    assert torch.equal(rm0, rm1) and rm0.abs().sum() > 0
