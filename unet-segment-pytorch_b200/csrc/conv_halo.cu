@@ -233,7 +233,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   }
 }
 
+int conv_halo2_launch(const ConvFwdArgs& a, cudaStream_t stream);   // conv_halo2.cu: cta_group::2 variant
+
 int conv_halo_launch(const ConvFwdArgs& a, cudaStream_t stream) {
+  if (g_conv_mode != 1) {
+    const int rc2 = conv_halo2_launch(a, stream);
+    if (rc2 != 1) return rc2;
+  }
   const int Ctot = a.C0 + a.C1;
   if (g_conv_mode == 1 || a.taps != 9 || a.W % 128 != 0 || a.C0 % 64 != 0 || Ctot % 64 != 0) return 1;
   // Cout > 128: the per-tap kernel with a 256-wide N tile is already tensor-bound (measured)
