@@ -116,6 +116,8 @@ WG_CASES = [
     (3, 9, 128, 64, 0, 32, 9),
     (1, 4, 128, 64, 0, 96, 9),
     (2, 16, 512, 64, 0, 64, 9),
+    (2, 6, 128, 128, 128, 128, 9),  # four channel chunks: two CTA pairs (cta_group::2 wgrad)
+    (1, 12, 256, 192, 64, 64, 9),   # 64-byte-swizzled half of dy per CTA
 ]
 
 

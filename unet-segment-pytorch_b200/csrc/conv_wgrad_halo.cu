@@ -234,7 +234,13 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
 }
 
 // returns 1 if the shape is not eligible (caller falls back to the per-tap kernel)
+int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream);   // conv_wgrad_halo2.cu
+
 int conv_wgrad_halo_launch(const ConvWgradArgs& a, cudaStream_t stream) {
+  {
+    const int rc2 = conv_wgrad_halo2_launch(a, stream);
+    if (rc2 != 1) return rc2;
+  }
   const int Ctot = a.C0 + a.C1;
   if (a.taps != 9 || a.W % 128 != 0 || a.C0 % 64 != 0 || Ctot % 64 != 0) return 1;
   if (a.Cout % 16 != 0 || a.Cout > 128 || a.splits_override > 0) return 1;
