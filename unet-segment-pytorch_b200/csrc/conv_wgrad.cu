@@ -226,6 +226,7 @@ static int pow2_floor_w(int x) {
 }
 
 int conv_wgrad_halo_launch(const ConvWgradArgs& a, cudaStream_t stream);
+int conv_wgrad2_launch(const ConvWgradArgs& a, cudaStream_t stream);
 extern int g_conv_mode_wgrad;
 
 int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
@@ -237,6 +238,10 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   if (a.taps != 1 && a.taps != 9) return UB2_ERR_SHAPE;
   if (a.N <= 0 || a.H <= 0 || a.W <= 0 || a.C0 <= 0 || a.C1 < 0) return UB2_ERR_SHAPE;
   if (Ctot % 16 != 0 || a.C0 % 16 != 0 || a.Cout % 16 != 0) return UB2_ERR_SHAPE;
+  if (g_conv_mode_wgrad != 1) {   // deep layers: two-CTA kernel sharing dy (conv_wgrad2.cu)
+    const int rc2 = conv_wgrad2_launch(a, stream);
+    if (rc2 != 1) return rc2;
+  }
   if (a.ld_in0 % 8 != 0 || (a.C1 > 0 && a.ld_in1 % 8 != 0) || a.ld_dy % 8 != 0) return UB2_ERR_ALIGN;
   int mc = 64;
   while (a.C0 % mc != 0 || Ctot % mc != 0) mc /= 2;
