@@ -227,10 +227,17 @@ static int pow2_floor(int x) {
   return r;
 }
 
+int conv_fwd2_launch(const ConvFwdArgs& a, cudaStream_t stream);   // conv_fwd2.cu: cta_group::2 variant
+
 int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   if (!a.tf32) {
     // wide 3x3 layers: halo block resident in shared memory (conv_halo.cu)
     const int rc = conv_halo_launch(a, stream);
+    if (rc != 1) return rc;
+  }
+  {
+    // the remaining bf16 layers with 64-channel chunks: two-CTA kernel sharing the weight tile
+    const int rc = conv_fwd2_launch(a, stream);
     if (rc != 1) return rc;
   }
   const int Ctot = a.C0 + a.C1;
