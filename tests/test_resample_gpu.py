@@ -15,6 +15,8 @@ CASES = [
     (2, 16, 16, 33, 33, 33, 33, 24),      # F.interpolate to an arbitrary size, C not a multiple of 16
     (1, 20, 24, 47, 55, 47, 55, 64),      # gate-style resize (scale ~0.41)
     (1, 1, 1, 2, 2, 2, 2, 16),
+    (1, 40, 36, 90, 80, 90, 80, 32),      # scale ~0.44, tall enough for the column-strip kernels
+    (3, 48, 32, 96, 64, 97, 66, 64),      # strips with a remainder (48 = 3 x 16), F.pad border
 ]
 
 

@@ -56,6 +56,64 @@ upsample_fwd_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, __nv_bfloat
   }
 }
 
+// Column-strip forward: a thread owns one destination column x 8 channels and walks kStripRows
+// destination rows, keeping the two horizontally interpolated source rows it is between in
+// registers (they change every other row for a 2x up-sampling).  ~50 instructions per 16-byte
+// output instead of ~230 (the per-pixel kernel above is issue bound: ncu issue-active 75 %).
+static constexpr int kStripRows = 16;
+
+__global__ void __launch_bounds__(256)
+upsample_fwd_strip_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, __nv_bfloat16* __restrict__ out,
+                          int ld_out, UpGeom g) {
+  const int wo = blockIdx.x * blockDim.y + threadIdx.y;
+  const int n = blockIdx.z;
+  if (wo >= g.Wo) return;
+  const int uw = wo - g.pl;
+  const bool col_inside = uw >= 0 && uw < g.wu;
+  int w0 = 0, w1 = 0;
+  float b0 = 0.f, b1 = 0.f;
+  if (col_inside) src_index(g.rw, uw, g.win, w0, w1, b0, b1);
+  const __nv_bfloat16* base = in + static_cast<size_t>(n) * g.hin * g.win * ld_in;
+  const int ho_begin = blockIdx.y * kStripRows;
+  const int ho_end = min(ho_begin + kStripRows, g.Ho);
+  for (int cg = threadIdx.x; cg < g.cgs; cg += blockDim.x) {
+    auto hrow = [&](int h) {   // source row h interpolated at this column
+      const F8 a = load8(base + (static_cast<size_t>(h) * g.win + w0) * ld_in + cg * 8);
+      const F8 b = load8(base + (static_cast<size_t>(h) * g.win + w1) * ld_in + cg * 8);
+      F8 r;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r.v[k] = b0 * a.v[k] + b1 * b.v[k];
+      return r;
+    };
+    int cur0 = -1, cur1 = -1;
+    F8 top, bot;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) top.v[k] = bot.v[k] = 0.f;
+    for (int ho = ho_begin; ho < ho_end; ++ho) {
+      const int uh = ho - g.pt;
+      F8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+      if (col_inside && uh >= 0 && uh < g.hu) {
+        int h0, h1;
+        float a0, a1;
+        src_index(g.rh, uh, g.hin, h0, h1, a0, a1);   // block-uniform
+        if (h0 != cur0) {
+          top = (h0 == cur1) ? bot : hrow(h0);
+          cur0 = h0;
+        }
+        if (h1 != cur1) {
+          bot = (h1 == cur0) ? top : hrow(h1);
+          cur1 = h1;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = a0 * top.v[k] + a1 * bot.v[k];
+      }
+      store8(out + ((static_cast<size_t>(n) * g.Ho + ho) * g.Wo + wo) * ld_out + cg * 8, o);
+    }
+  }
+}
+
 // weight with which up-sampled index `u` reads source index `i`
 __device__ __forceinline__ float tap_weight(float r, int u, int in, int i) {
   int i0, i1;
@@ -248,6 +306,104 @@ static bool bwd_tiled_ok(const UpGeom& g) {
   return span_h <= kBT_RH && span_w <= kBT_RW && g.rw >= 0.4f && g.rh >= 0.4f;
 }
 
+// Column-strip transpose for real up-sampling (0.4 <= scale <= 0.6 on both axes): a thread owns one
+// SOURCE column x 8 channels and a strip of kBwdStrip source rows; it walks the destination rows
+// that touch the strip once, reduces each horizontally (<= 5 hat-weighted taps) and adds the result
+// to the two source rows it lies between, which are kept in registers and written when the walk has
+// passed them.  ~220 instructions per 16-byte output instead of ~1000 for the gather kernels (both
+// were issue bound), deterministic, no shared memory.
+static constexpr int kBwdStrip = 16;
+
+__global__ void __launch_bounds__(256)
+upsample_bwd_strip_kernel(const __nv_bfloat16* __restrict__ dout, int ld_dout, __nv_bfloat16* __restrict__ din,
+                          int ld_din, int accumulate, UpGeom g) {
+  const int j = blockIdx.x * blockDim.y + threadIdx.y;   // source column
+  const int n = blockIdx.z;
+  if (j >= g.win) return;
+  const int ia = blockIdx.y * kBwdStrip, ib = min(ia + kBwdStrip, g.hin);
+  // column taps: destination columns v0 .. v0+4 (see upsample_bwd_tiled_kernel)
+  const float fj = static_cast<float>(j);
+  int v0 = static_cast<int>(floorf((fj - 1.f) / g.rw)) + 1;
+  if (v0 < 0) v0 = 0;
+  float wv[5];
+  int cv[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int v = v0 + k;
+    wv[k] = (v < g.wu) ? fmaxf(0.f, 1.f - fabsf(g.rw * static_cast<float>(v) - fj)) : 0.f;
+    cv[k] = min(v, g.wu - 1) + g.pl;
+  }
+  // destination rows whose upper tap is one of the rows ia-1 .. ib-1 (block-uniform, with margins;
+  // the exact classification below uses ATen's own index arithmetic)
+  int u_lo = static_cast<int>(floorf(static_cast<float>(ia - 1) / g.rh)) - 1;
+  int u_hi = static_cast<int>(ceilf(static_cast<float>(ib) / g.rh)) + 1;
+  if (u_lo < 0) u_lo = 0;
+  if (u_hi > g.hu - 1) u_hi = g.hu - 1;
+  const __nv_bfloat16* src = dout + static_cast<size_t>(n) * g.Ho * g.Wo * ld_dout;
+  __nv_bfloat16* dst = din + (static_cast<size_t>(n) * g.hin * g.win + j) * ld_din;
+  for (int cg = threadIdx.x; cg < g.cgs; cg += blockDim.x) {
+    auto flush = [&](int row, const F8& acc) {
+      if (row < ia || row >= ib) return;
+      __nv_bfloat16* q = dst + static_cast<size_t>(row) * g.win * ld_din + cg * 8;
+      F8 o = acc;
+      if (accumulate) {
+        const F8 old = load8(q);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] += old.v[k];
+      }
+      store8(q, o);
+    };
+    F8 acc0, acc1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc0.v[k] = acc1.v[k] = 0.f;
+    int r_cur = -2;
+    for (int u = u_lo; u <= u_hi; ++u) {
+      int i0, i1;
+      float l0, l1;
+      src_index(g.rh, u, g.hin, i0, i1, l0, l1);
+      if (i0 < ia - 1 || i0 > ib - 1) continue;   // touches no row of this strip
+      if (r_cur == -2) r_cur = i0;
+      while (i0 > r_cur) {                          // the walk has passed row r_cur
+        flush(r_cur, acc0);
+        acc0 = acc1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc1.v[k] = 0.f;
+        ++r_cur;
+      }
+      const __nv_bfloat16* rowp = src + static_cast<size_t>(u + g.pt) * g.Wo * ld_dout + cg * 8;
+      F8 t;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t.v[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        if (wv[k] != 0.f) {
+          const F8 d = load8(rowp + static_cast<size_t>(cv[k]) * ld_dout);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) t.v[c] = fmaf(wv[k], d.v[c], t.v[c]);
+        }
+      }
+      if (i1 == i0) {   // clamped last row: both taps are the same source row
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc0.v[k] = fmaf(l0 + l1, t.v[k], acc0.v[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc0.v[k] = fmaf(l0, t.v[k], acc0.v[k]);
+          acc1.v[k] = fmaf(l1, t.v[k], acc1.v[k]);
+        }
+      }
+    }
+    if (r_cur != -2) {
+      flush(r_cur, acc0);
+      flush(r_cur + 1, acc1);
+    }
+  }
+}
+
+static bool bwd_strip_ok(const UpGeom& g) {
+  return g.rh >= 0.4f && g.rh <= 0.6f && g.rw >= 0.4f && g.rw <= 0.6f && g.hin >= 2 * kBwdStrip;
+}
+
 static dim3 up_block(int cgs) {
   int bx = 1;
   while (bx < cgs && bx < 256) bx *= 2;
@@ -276,6 +432,13 @@ int ub2_upsample_fwd(const void* in, int ld_in, void* out, int ld_out, int N, in
   if (C % 8 != 0 || Ho < hu || Wo < wu || N <= 0) return UB2_ERR_SHAPE;
   if (ld_in % 8 || ld_out % 8) return UB2_ERR_ALIGN;
   UpGeom g = up_geom(N, hin, win, hu, wu, Ho, Wo, C);
+  if (Ho >= 2 * kStripRows) {
+    const dim3 sblock = up_block(g.cgs);
+    const dim3 sgrid((Wo + sblock.y - 1) / sblock.y, (Ho + kStripRows - 1) / kStripRows, N);
+    upsample_fwd_strip_kernel<<<sgrid, sblock, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, g);
+    return static_cast<int>(cudaGetLastError());
+  }
   const dim3 block = up_block(g.cgs);
   const dim3 grid((Wo + block.y - 1) / block.y, Ho, N);
   upsample_fwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -288,6 +451,13 @@ int ub2_upsample_bwd(const void* dout, int ld_dout, void* din, int ld_din, int a
   if (C % 8 != 0 || Ho < hu || Wo < wu || N <= 0) return UB2_ERR_SHAPE;
   if (ld_dout % 8 || ld_din % 8) return UB2_ERR_ALIGN;
   UpGeom g = up_geom(N, hin, win, hu, wu, Ho, Wo, C);
+  if (bwd_strip_ok(g)) {
+    const dim3 sblock = up_block(g.cgs);
+    const dim3 sgrid((win + sblock.y - 1) / sblock.y, (hin + kBwdStrip - 1) / kBwdStrip, N);
+    upsample_bwd_strip_kernel<<<sgrid, sblock, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din, accumulate, g);
+    return static_cast<int>(cudaGetLastError());
+  }
   if (bwd_tiled_ok(g)) {
     const int slabs = C / 16;
     const dim3 tgrid((win + kBT_W - 1) / kBT_W, (hin + kBT_H - 1) / kBT_H, N * slabs);
