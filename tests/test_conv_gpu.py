@@ -118,6 +118,8 @@ WG_CASES = [
     (2, 16, 512, 64, 0, 64, 9),
     (2, 6, 128, 128, 128, 128, 9),  # four channel chunks: two CTA pairs (cta_group::2 wgrad)
     (1, 12, 256, 192, 64, 64, 9),   # 64-byte-swizzled half of dy per CTA
+    (2, 7, 128, 64, 0, 128, 9),     # single channel chunk: the CTA pair splits the taps
+    (1, 5, 256, 64, 0, 64, 9),
     # deep layers: two-CTA per-tap kernel (Cout a multiple of 128)
     (1, 16, 16, 128, 0, 256, 9),    # 9 M tiles: odd, the last pair has a phantom tile
     (2, 8, 8, 256, 256, 128, 1),    # 1x1, two sources

@@ -36,6 +36,11 @@ struct WgHalo2Params {
   int bn_cols, kchunks, tapgroups, splits, per_split, blocks, segs_w, blocks_h;
   int a_bytes, b_stage_bytes, b_stages, tmem_cols;
   int half;   // dy channels streamed by each CTA (Cout / 2: 64 -> 128-byte rows, 32 -> 64-byte rows)
+  // Single channel chunk (C0 + C1 == 64): the pair splits the TAPS instead.  Both CTAs issue the
+  // same three tap pairs (virtual taps 0..5); the peer's halo block is loaded two image rows lower,
+  // so its virtual taps 0,1,2 are the real taps 6,7,8 (its other three tiles are discarded):
+  // three MMA pairs per k-step instead of five, and each CTA streams half of dy.
+  int tapsplit;
   float* partial;
 };
 
@@ -91,13 +96,21 @@ conv_wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   const uint32_t tmem_base = hdr->tmem_base;
 
   // pair item -> (two neighbouring channel chunks, tap group, split); this CTA owns chunk 2k + rank
-  const int pair_groups = (p.kchunks / 2) * p.tapgroups;
+  const int pair_groups = p.tapsplit ? 1 : (p.kchunks / 2) * p.tapgroups;
   const int items = pair_groups * p.splits;   // (shadows the one-CTA item count above)
   const int cluster_id = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
+  const int tap_shift = p.tapsplit ? 6 * static_cast<int>(rank) : 0;   // real tap = virtual tap + tap_shift
+  const int row_shift = p.tapsplit ? 2 * static_cast<int>(rank) : 0;   // image rows the halo block starts lower
   auto decode_item = [&](int it, int& c, int& t_begin, int& t_end, int& sp) {
     sp = it / pair_groups;
     const int g = it % pair_groups;
+    if (p.tapsplit) {
+      c = 0;
+      t_begin = 0;
+      t_end = 6;
+      return;
+    }
     c = (2 * (g % (p.kchunks / 2)) + static_cast<int>(rank)) * 64;
     const int tg = g / (p.kchunks / 2);
     if (p.tapgroups == 1) { t_begin = 0; t_end = 9; }
@@ -126,9 +139,9 @@ conv_wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
           const uint32_t bar = mapa_u32(smem_u32(&hdr->a_full[abuf]), 0);
           if (leader) mbar_expect_tx(&hdr->a_full[abuf], 2 * a_tx);
           if (c < p.C0)
-            tma2_load_4d(sA + abuf * p.a_bytes, &tmA0, bar, c, w0 - 1, h0 - 1, n);
+            tma2_load_4d(sA + abuf * p.a_bytes, &tmA0, bar, c, w0 - 1, h0 - 1 + row_shift, n);
           else
-            tma2_load_4d(sA + abuf * p.a_bytes, &tmA1, bar, c - p.C0, w0 - 1, h0 - 1, n);
+            tma2_load_4d(sA + abuf * p.a_bytes, &tmA1, bar, c - p.C0, w0 - 1, h0 - 1 + row_shift, n);
         }
         if (++abuf == 2) { abuf = 0; aphase ^= 1; }
         for (int kc = 0; kc < 2 * R; ++kc) {  // 64-pixel pieces: row kc/2, half kc%2
@@ -219,8 +232,9 @@ conv_wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
       mbar_wait(&hdr->tmem_full, n_it & 1);
       tc_fence_after();
       for (int pr = 0; pr < npairs; ++pr) {
-        const int tap = t_begin + 2 * pr + (row >> 6);
-        const bool rvalid = tap < t_end;
+        const int vtap = t_begin + 2 * pr + (row >> 6);
+        const int tap = vtap + tap_shift;
+        const bool rvalid = vtap < t_end && tap < 9;
         const int m = tap * Ctot + c + (row & 63);
         float* dst = p.partial + (static_cast<size_t>(sp) * Mtot + m) * p.Cout;
         for (int j = 0; j < p.bn_cols / 32; ++j) {
@@ -262,7 +276,10 @@ conv_wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
 int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   static const int enabled = [] { const char* e = getenv("UB2_WGRAD2"); return e ? atoi(e) : 1; }();
   const int Ctot = a.C0 + a.C1;
-  if (!enabled || a.taps != 9 || a.W % 128 != 0 || a.C0 % 64 != 0 || Ctot % 128 != 0) return 1;
+  // tap split (Ctot == 64) only pays at Cout = 128: both CTAs load the same halo block, and at
+  // Cout = 64 that doubled activation traffic outweighs the saved MMAs (measured: 0.68 -> 0.75 ms)
+  if (!enabled || a.taps != 9 || a.W % 128 != 0 || a.C0 % 64 != 0) return 1;
+  if (Ctot % 128 != 0 && !(Ctot == 64 && a.Cout == 128)) return 1;
   if ((a.Cout != 64 && a.Cout != 128) || a.splits_override > 0) return 1;
   if (a.ld_in0 % 8 != 0 || (a.C1 > 0 && a.ld_in1 % 8 != 0) || a.ld_dy % 8 != 0) return UB2_ERR_ALIGN;
 
@@ -270,8 +287,9 @@ int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   p.N = a.N; p.H = a.H; p.W = a.W; p.C0 = a.C0; p.C1 = a.C1; p.Cout = a.Cout;
   p.bn_cols = (a.Cout + 31) & ~31;
   p.kchunks = Ctot / 64;
-  p.tapgroups = (5 * p.bn_cols <= 512) ? 1 : 2;   // five / three 128-row tiles of bn_cols columns in TMEM
-  const int tiles = p.tapgroups == 1 ? 5 : 3;
+  p.tapsplit = Ctot == 64;
+  p.tapgroups = (p.tapsplit || 5 * p.bn_cols <= 512) ? 1 : 2;   // five / three 128-row tiles of bn_cols columns in TMEM
+  const int tiles = (p.tapsplit || p.tapgroups == 2) ? 3 : 5;
   int tmem_cols = 32;
   while (tmem_cols < tiles * p.bn_cols) tmem_cols *= 2;
   p.tmem_cols = tmem_cols;
@@ -305,7 +323,7 @@ int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     }
     max_clusters = n;
   }
-  const int groups = (p.kchunks / 2) * p.tapgroups;   // cluster work items per split
+  const int groups = p.tapsplit ? 1 : (p.kchunks / 2) * p.tapgroups;   // cluster work items per split
   int splits = max_clusters / groups;
   if (splits < 1) splits = 1;
   if (splits > p.blocks) splits = p.blocks;
