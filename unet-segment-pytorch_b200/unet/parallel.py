@@ -79,6 +79,8 @@ class BatchShardedTrainer:
         self.graph_warmup = graph_warmup
         self._graphs = {}
         self._eager_steps = {}
+        self._copy_stream = None   # mask copies (see step)
+        self._masks_ready = self._step_done = None
 
     # ------------------------------------------------------------------ flat gradient buckets
     def _build_buckets(self, bucket_mb: float) -> None:
@@ -147,7 +149,9 @@ class BatchShardedTrainer:
             self._bucket_ready(b)
 
     # ------------------------------------------------------------------ one optimizer step
-    def _step_body(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+    def _forward(self, images: torch.Tensor):
+        """First half of a step: zero the gradient buckets, rebuild the weight packs (one launch)
+        and run the model's forward pass.  Does not touch the masks."""
         self.model.train()
         for b in self.buckets:
             b.flat.zero_()
@@ -161,15 +165,21 @@ class BatchShardedTrainer:
                 self._packer = WeightPacker([m.weight for m in self.model.modules()
                                              if isinstance(m, torch.nn.Conv2d) and m.weight.is_cuda])
             self._packer.run()
-        prev_sink, prev_packs = ops.GRAD_SINK, ops.PACKS
-        ops.GRAD_SINK, ops.PACKS = _GradSink(self), self._packer
+        prev_packs, ops.PACKS = ops.PACKS, self._packer
         try:
-            outputs = self.model(images)
+            return self.model(images)
+        finally:
+            ops.PACKS = prev_packs
+
+    def _backward(self, outputs, masks: torch.Tensor) -> torch.Tensor:
+        """Second half: loss, backward (gradient sink installed), all-reduce, clip + optimizer, EMA."""
+        prev_sink, ops.GRAD_SINK = ops.GRAD_SINK, _GradSink(self)
+        try:
             loss = self.criterion(outputs, masks)
             (loss / self.world).backward()
             self._flush_deferred()
         finally:
-            ops.GRAD_SINK, ops.PACKS = prev_sink, prev_packs
+            ops.GRAD_SINK = prev_sink
         if self.world > 1:
             for b in self.buckets:
                 if b.work is None:  # a parameter without gradient this step
@@ -188,6 +198,9 @@ class BatchShardedTrainer:
             self.ema.update(self.model, _advance=False)
         return loss.detach()
 
+    def _step_body(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        return self._backward(self._forward(images), masks)
+
     def _optimizer_capturable(self) -> bool:
         if isinstance(self.optimizer, FusedAdamW):
             return True
@@ -202,8 +215,24 @@ class BatchShardedTrainer:
         if self.ema is not None:
             self.ema.prepare(self.model)   # host side: counter, warm-up decay -> device memory
         use_graph = self.cuda_graph and dev.type == "cuda" and self._optimizer_capturable()
+        if dev.type != "cuda":
+            return self._step_body(images.to(dev), masks.to(dev))
+        # The masks are not needed before the loss: their host->device copy (8 of the 12.5 MB of a
+        # batch-4 step) runs on a copy stream under the forward pass.
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._masks_ready = torch.cuda.Event()
+            self._step_done = torch.cuda.Event()
+        copy = self._copy_stream
         if not use_graph:
-            return self._step_body(images.to(dev, non_blocking=True), masks.to(dev, non_blocking=True))
+            with torch.cuda.stream(copy):
+                masks_dev = masks.to(dev, non_blocking=True)
+                self._masks_ready.record(copy)
+            outputs = self._forward(images.to(dev, non_blocking=True))
+            main.wait_event(self._masks_ready)
+            masks_dev.record_stream(main)
+            return self._backward(outputs, masks_dev)
         key = (tuple(images.shape), images.dtype, tuple(masks.shape), masks.dtype)
         entry = self._graphs.get(key)
         if entry is None:
@@ -213,27 +242,39 @@ class BatchShardedTrainer:
                 # torch.cuda.graph requires
                 self._eager_steps[key] = done + 1
                 side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
+                side.wait_stream(main)
                 with torch.cuda.stream(side):
                     loss = self._step_body(images.to(dev, non_blocking=True), masks.to(dev, non_blocking=True))
-                torch.cuda.current_stream(dev).wait_stream(side)
+                main.wait_stream(side)
                 return loss
             gx = torch.empty(images.shape, dtype=images.dtype, device=dev)
             gt = torch.empty(masks.shape, dtype=masks.dtype, device=dev)
             gx.copy_(images, non_blocking=True)
             gt.copy_(masks, non_blocking=True)
             torch.cuda.synchronize(dev)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                gloss = self._step_body(gx, gt)
-            entry = self._graphs[key] = (graph, gx, gt, gloss)
+            # two graphs sharing one memory pool, always replayed in this order: forward | the rest.
+            # Between them the main stream waits for the masks.
+            g_fwd, g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fwd):
+                outputs = self._forward(gx)
+            with torch.cuda.graph(g_bwd, pool=g_fwd.pool()):
+                gloss = self._backward(outputs, gt)
+            del outputs
+            entry = self._graphs[key] = (g_fwd, g_bwd, gx, gt, gloss)
+            self._step_done.record(main)
             # the capture itself does not execute: fall through and replay it for this step
-        graph, gx, gt, gloss = entry
+        g_fwd, g_bwd, gx, gt, gloss = entry
         gx.copy_(images, non_blocking=True)
-        gt.copy_(masks, non_blocking=True)
+        copy.wait_event(self._step_done)          # the previous replay has finished reading `gt`
+        with torch.cuda.stream(copy):
+            gt.copy_(masks, non_blocking=True)
+            self._masks_ready.record(copy)
         if isinstance(self.optimizer, FusedAdamW):
             self.optimizer.sync_hyperparams()   # a scheduler may have changed the learning rate
-        graph.replay()
+        g_fwd.replay()
+        main.wait_event(self._masks_ready)
+        g_bwd.replay()
+        self._step_done.record(main)
         return gloss
 
     def release_graphs(self) -> None:
