@@ -140,6 +140,8 @@ int ub2_upsample_bwd(const void* dout, int ld_dout, void* din, int ld_din, int a
 /* q = W_g.g at low resolution and xp = W_x.x come from ub2_conv_fwd (taps = 1).           */
 
 int ub2_gate_rows(int N, int H, int W, int C);
+/* rows for ub2_gate_upstats / ub2_gate_psi / ub2_gate_bwd_s (one per block of their strip grid) */
+int ub2_gate_strip_rows(int N, int H, int W, int C);
 /* Batch statistics of F.interpolate(q, (H,W), bilinear, align_corners=True) for BN_g
  * (layers.py:183,186) without materialising the up-sampled tensor. */
 int ub2_gate_upstats(const void* q, int ld_q, int N, int hin, int win, int H, int W, int Ci,

@@ -27,8 +27,10 @@ static constexpr int kMaxG = 2;  // 8-channel groups per thread (channels <= 512
 struct GateGeom {
   int N, H, W, C, cgs, tpp, slots;
   int pixels;
+  int wt, ht;   // strip kernels: column tiles of `slots` pixels x row strips of kGateStrip rows
   LowRes lr;
 };
+static constexpr int kGateStrip = 16;
 
 static int gate_tpp(int cgs) {
   int t = 1;
@@ -43,9 +45,12 @@ static int make_gate_geom(GateGeom* g, int N, int H, int W, int C, int hin, int 
   if ((g->cgs + g->tpp - 1) / g->tpp > kMaxG) return UB2_ERR_SHAPE;
   g->slots = kGateThreads / g->tpp;
   g->pixels = static_cast<int>(N) * H * W;
+  g->wt = (W + g->slots - 1) / g->slots;
+  g->ht = (H + kGateStrip - 1) / kGateStrip;
   g->lr = make_lowres(hin > 0 ? hin : 1, win > 0 ? win : 1, H, W);
   return 0;
 }
+static int gate_strip_grid(const GateGeom& g) { return g.wt * g.ht * g.N; }
 static int gate_grid(const GateGeom& g, int per_sm) {
   return stream_grid(g.pixels, g.slots, num_sms(), per_sm);
 }
@@ -114,6 +119,83 @@ __device__ __forceinline__ void block_reduce_scalars(float (&acc)[NS], double* o
   const int ho = static_cast<int>((pix / (g).W) % (g).H);                     \
   const int n = static_cast<int>(pix / (static_cast<int>((g).W) * (g).H));
 
+// Strip walk for the passes that need up(q): a block owns `slots` columns x kGateStrip rows of one
+// image, a thread one column (x `tpp` lanes over the channels) and walks the rows.  No per-pixel
+// integer division, and the two horizontally interpolated low-resolution rows a destination row lies
+// between stay in registers (they change every other row for a 2x up-sampling).  ncu on the
+// per-pixel form: ~320 instructions per pixel-vector, half of them integer address arithmetic.
+template <int G>
+struct QRoll {
+  int cur0, cur1, w0, w1;
+  float a0, a1, b0, b1;
+  F8 top[G], bot[G];
+};
+template <int G>
+__device__ __forceinline__ void qroll_init(QRoll<G>& r, const GateGeom& g, int wo) {
+  r.cur0 = r.cur1 = -1;
+  src_index(g.lr.rw, wo < g.W ? wo : g.W - 1, g.lr.win, r.w0, r.w1, r.b0, r.b1);
+#pragma unroll
+  for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.top[gi].v[k] = r.bot[gi].v[k] = 0.f;
+}
+template <int G>
+__device__ __forceinline__ void qroll_row(QRoll<G>& r, const __nv_bfloat16* __restrict__ q, int ld_q,
+                                          const GateGeom& g, int n, int ho, int j, bool colv) {
+  int h0, h1;
+  src_index(g.lr.rh, ho, g.lr.hin, h0, h1, r.a0, r.a1);   // block-uniform
+  const __nv_bfloat16* base = q + static_cast<size_t>(n) * g.lr.hin * g.lr.win * ld_q;
+  auto hrow = [&](int h, int gi) {
+    F8 o;
+    const int cg = j + gi * g.tpp;
+    if (colv && cg < g.cgs) {
+      const F8 a = load8(base + (static_cast<size_t>(h) * g.lr.win + r.w0) * ld_q + cg * 8);
+      const F8 b = load8(base + (static_cast<size_t>(h) * g.lr.win + r.w1) * ld_q + cg * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = r.b0 * a.v[k] + r.b1 * b.v[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+    }
+    return o;
+  };
+  if (h0 != r.cur0) {
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) r.top[gi] = (h0 == r.cur1) ? r.bot[gi] : hrow(h0, gi);
+    r.cur0 = h0;
+  }
+  if (h1 != r.cur1) {
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) r.bot[gi] = (h1 == r.cur0) ? r.top[gi] : hrow(h1, gi);
+    r.cur1 = h1;
+  }
+}
+template <int G>
+__device__ __forceinline__ F8 qroll_get(const QRoll<G>& r, int gi) {
+  F8 u;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) u.v[k] = r.a0 * r.top[gi].v[k] + r.a1 * r.bot[gi].v[k];
+  return u;
+}
+
+// for (row of the strip) { pix, pv, u = up(q) at this pixel via qroll_get(roll, gi) }
+#define GATE_STRIP_LOOP(g, G_)                                                               \
+  const int slot = threadIdx.x / (g).tpp;                                                    \
+  const int j = threadIdx.x % (g).tpp;                                                       \
+  const int bw_ = static_cast<int>(blockIdx.x) % (g).wt;                                     \
+  const int bh_ = (static_cast<int>(blockIdx.x) / (g).wt) % (g).ht;                          \
+  const int n = static_cast<int>(blockIdx.x) / ((g).wt * (g).ht);                            \
+  const int wo = bw_ * (g).slots + slot;                                                     \
+  const bool pv = wo < (g).W;                                                                \
+  QRoll<G_> roll;                                                                            \
+  qroll_init<G_>(roll, g, wo);                                                               \
+  const int ho_end_ = min((bh_ + 1) * kGateStrip, (g).H);                                    \
+  for (int ho = bh_ * kGateStrip; ho < ho_end_; ++ho)
+
+#define GATE_STRIP_ROW(g, G_)                                                                \
+  const int pix = (n * (g).H + ho) * (g).W + (pv ? wo : 0);                                  \
+  qroll_row<G_>(roll, q, ld_q, g, n, ho, j, pv);
+
 // ------------------------------------------------------------------------------ forward
 template <int G>
 __global__ void __launch_bounds__(kGateThreads)
@@ -126,14 +208,14 @@ gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* parti
     for (int b = 0; b < 2; ++b)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[a][b][k] = 0.f;
-  GATE_PIXEL_LOOP(g) {
-    GATE_PIX(g)
-    GATE_DECODE(g)
+  GATE_STRIP_LOOP(g, G) {
+    GATE_STRIP_ROW(g, G)
+    (void)pix;
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
-        const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
+        const F8 u = qroll_get<G>(roll, gi);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           acc[gi][0][k] += u.v[k];
@@ -175,16 +257,15 @@ gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat
   __shared__ float smem[kGateThreads / 32];
   float st[2] = {0.f, 0.f};
   const GateVec v0 = gate_vec(sg, hg, sx, hx, wpsi, threadIdx.x % g.tpp, g.cgs);
-  GATE_PIXEL_LOOP(g) {
-    GATE_PIX(g)
-    GATE_DECODE(g)
+  GATE_STRIP_LOOP(g, G) {
+    GATE_STRIP_ROW(g, G)
     float dot = 0.f;
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
         const GateVec v = (gi == 0) ? v0 : gate_vec(sg, hg, sx, hx, wpsi, cg, g.cgs);
-        const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
+        const F8 u = qroll_get<G>(roll, gi);
         const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -303,9 +384,8 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[a][b][k] = 0.f;
-  GATE_PIXEL_LOOP(g) {
-    GATE_PIX(g)
-    GATE_DECODE(g)
+  GATE_STRIP_LOOP(g, G) {
+    GATE_STRIP_ROW(g, G)
     // BN_psi backward: d psi_raw = A*dn + B*psi_raw + C
     const float dpr = pv ? fmaf(cA, __ldg(dpsin + pix), fmaf(cB, __ldg(psi_raw + pix), cC)) : 0.f;
 #pragma unroll
@@ -313,7 +393,7 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
         const GateVec v = (gi == 0) ? v0 : gate_vec(sg, hg, sx, hx, wpsi, cg, g.cgs);
-        const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
+        const F8 u = qroll_get<G>(roll, gi);
         const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
         F8 o;
 #pragma unroll
@@ -386,16 +466,15 @@ gate_bwd_xg_kernel(const __nv_bfloat16* __restrict__ ds, int ld_ds, const __nv_b
 #pragma unroll
       for (int k = 0; k < 8; ++k) cf[r].v[k] = __ldg(coef + r * g.C + (cg0 < g.cgs ? cg0 : 0) * 8 + k);
   }
-  GATE_PIXEL_LOOP(g) {
-    GATE_PIX(g)
-    GATE_DECODE(g)
+  GATE_STRIP_LOOP(g, G) {
+    GATE_STRIP_ROW(g, G)
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
       const int cg = j + gi * g.tpp;
       if (pv && cg < g.cgs) {
         const F8 d = load8_stream(ds + static_cast<size_t>(pix) * ld_ds + cg * 8);
         const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
-        const F8 u = interp8(q, ld_q, g.lr, n, ho, wo, cg);
+        const F8 u = qroll_get<G>(roll, gi);
         F8 ox, og;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -431,12 +510,19 @@ int ub2_gate_rows(int N, int H, int W, int C) {
   return gate_grid(g, 8);
 }
 
+int ub2_gate_strip_rows(int N, int H, int W, int C) {
+  GateGeom g;
+  int rc = make_gate_geom(&g, N, H, W, C, 1, 1);
+  if (rc) return rc;
+  return gate_strip_grid(g);
+}
+
 int ub2_gate_upstats(const void* q, int ld_q, int N, int hin, int win, int H, int W, int Ci,
                      double* partials, int rows, void* stream) {
   GateGeom g;
   int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
   if (rc) return rc;
-  const int grid = gate_grid(g, 8);
+  const int grid = gate_strip_grid(g);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   if (g.cgs > g.tpp)
     gate_upstats_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<cbf>(q), ld_q, partials, g);
@@ -452,7 +538,7 @@ int ub2_gate_psi(const void* q, int ld_q, const void* xp, int ld_xp, const float
   GateGeom g;
   int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
   if (rc) return rc;
-  const int grid = gate_grid(g, 8);
+  const int grid = gate_strip_grid(g);
   if (partials != nullptr && grid != rows) return UB2_ERR_WORKSPACE;
   if (g.cgs > g.tpp)
     gate_psi_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -504,7 +590,7 @@ int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_p
   GateGeom g;
   int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
   if (rc) return rc;
-  const int grid = gate_grid(g, 8);
+  const int grid = gate_strip_grid(g);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   if (g.cgs > g.tpp)
     gate_bwd_s_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -535,7 +621,7 @@ int ub2_gate_bwd_xg(const void* ds, int ld_ds, const void* xp, int ld_xp, const 
   GateGeom g;
   int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
   if (rc) return rc;
-  const int grid = gate_grid(g, 8);
+  const int grid = gate_strip_grid(g);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (g.cgs > g.tpp)
     gate_bwd_xg_kernel<2><<<grid, kGateThreads, 0, s>>>(static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp,

@@ -294,9 +294,13 @@ def gate_rows(n, h, w, c):
     return _rows("ub2_gate_rows", n, h, w, c)
 
 
+def gate_strip_rows(n, h, w, c):
+    return _rows("ub2_gate_strip_rows", n, h, w, c)
+
+
 def gate_upstats(q, h, w):
     n, hin, win, ci, ld = _nhwc(q)
-    rows = gate_rows(n, h, w, ci)
+    rows = gate_strip_rows(n, h, w, ci)
     partials = torch.empty((rows, 2, ci), device=q.device, dtype=F64)
     _C.call("ub2_gate_upstats", ptr(q), ld, n, hin, win, h, w, ci, ptr(partials), rows, stream())
     return partials
@@ -306,7 +310,7 @@ def gate_psi(q, xp, sg, hg, sx, hx, wpsi, stats=True):
     n, hin, win, ci, ld_q = _nhwc(q)
     _, h, w, _, ld_xp = _nhwc(xp)
     psi = torch.empty((n, h, w), device=q.device, dtype=F32)
-    rows = gate_rows(n, h, w, ci)
+    rows = gate_strip_rows(n, h, w, ci)
     partials = torch.empty((rows, 2, 1), device=q.device, dtype=F64) if stats else None
     _C.call("ub2_gate_psi", ptr(q), ld_q, ptr(xp), ld_xp, ptr(sg), ptr(hg), ptr(sx), ptr(hx), ptr(wpsi),
             ptr(psi), ptr(partials), rows, n, hin, win, h, w, ci, stream())
@@ -338,7 +342,7 @@ def gate_bwd_s(dpsin, psi, coef_psi, q, xp, sg, hg, sx, hx, wpsi):
     n, hin, win, ci, ld_q = _nhwc(q)
     _, h, w, _, ld_xp = _nhwc(xp)
     ds = empty_nhwc(n, h, w, ci, q.device)
-    rows = gate_rows(n, h, w, ci)
+    rows = gate_strip_rows(n, h, w, ci)
     partials = torch.empty((rows, 4, ci), device=q.device, dtype=F64)
     _C.call("ub2_gate_bwd_s", ptr(dpsin), ptr(psi), ptr(coef_psi), ptr(q), ld_q, ptr(xp), ld_xp, ptr(sg),
             ptr(hg), ptr(sx), ptr(hx), ptr(wpsi), ptr(ds), ci, ptr(partials), rows, n, hin, win, h, w, ci,
