@@ -82,6 +82,31 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def synthetic_batch(n, h, w, seed):
+    """CT-shaped synthetic inputs: images ~ clamp(randn, -1, 1) (the reference feeds
+    (px/255 - 0.5)/0.5, unet/data/dataset.py:146); int64 masks with 1-3 filled ellipses covering
+    ~0.36 % of the pixels (README.md:135), ~10 % of the images left empty."""
+    import math
+
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 1, h, w, generator=g).clamp_(-1, 1)
+    t = torch.zeros(n, h, w, dtype=torch.long)
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    for i in range(n):
+        if torch.rand((), generator=g).item() < 0.1:
+            continue
+        k = int(torch.randint(1, 4, (), generator=g).item())
+        area = 0.0036 * h * w / k
+        for _ in range(k):
+            cy, cx = torch.rand((), generator=g).item() * h, torch.rand((), generator=g).item() * w
+            ratio = 0.5 + torch.rand((), generator=g).item()
+            ry, rx = max(1.0, math.sqrt(area / math.pi * ratio)), max(1.0, math.sqrt(area / math.pi / ratio))
+            t[i][((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0] = 1
+    return x, t
+
+
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_train_step_throughput(batch: int, steps: int, warmup: int):
     """The oracle's train step (fp32 CPU PyTorch) on all host cores; returns (img/s, cores, s/step)."""
@@ -180,8 +205,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from oracle import unet_oracle as O  # synthetic data generator only
-    from unet import _C, kernels as K
+    from unet import _C, kernels as K   # the GPU arm never touches oracle/
     from unet.models import AttentionUNet
     from unet.optim import FusedAdamW
     from unet.parallel import BatchShardedTrainer
@@ -194,7 +218,7 @@ def run_ours(args):
     opt = FusedAdamW(model.parameters(), lr=5e-5, weight_decay=1e-4)   # train.py:346-350, fused with the clip
     trainer = BatchShardedTrainer(model, criterion, opt, grad_clip=1.0, cuda_graph=not args.no_graph)
 
-    x_host, t_host = O.synthetic_batch(B, H, W, seed=1234 + rank)
+    x_host, t_host = synthetic_batch(B, H, W, seed=1234 + rank)
     x_host, t_host = x_host.pin_memory(), t_host.pin_memory()
     x_dev, t_dev = x_host.to(dev), t_host.to(dev)
 
