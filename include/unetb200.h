@@ -264,6 +264,25 @@ int ub2_adamw_step(const long long* ptrs, const long long* numel, const int* gro
  * 2: copy int64)}; chunks (nchunks,2) int32 as for ub2_adamw_step; *decay fp32 in device memory. */
 int ub2_ema_update(const long long* desc, const int* chunks, int nchunks, const float* decay, void* stream);
 
+/* ======================= either side of the forward pass ============ */
+
+/* LungTumorDataset.__getitem__ + the albumentations-free transform (unet/data/dataset.py:146-171,
+ * unet/data/augmentations.py:117-170) and preprocess_image (scripts/predict.py:100-136) for a
+ * batch of already-sized slices: images / labels uint8 (N,H,W) in device memory ->
+ * x fp32 (N,1,H,W) = ((px/255) - mean)/std, targets int64 (N,H,W) = label > 127.
+ * flags uint8 (N) or NULL: bit 0 horizontal flip (augmentations.py:160-162), bit 1 vertical flip.
+ * Bit-exact with numpy's float32 arithmetic (the transform's second uint8 round trip,
+ * augmentations.py:148, is the identity on all 256 levels).  labels and targets may both be NULL
+ * (inference). */
+int ub2_prepare_batch(const unsigned char* images, const unsigned char* labels, const unsigned char* flags,
+                      int N, int H, int W, float mean, float std, float* x, long long* targets,
+                      void* stream);
+/* postprocess_mask + tumor_ratio (scripts/predict.py:138-166, 232-240) for a batch: logits fp32
+ * (N,2,H,W) -> mask uint8 (N,H,W) = 255 * (softmax(logits)[1] > threshold), positives int32 (N) =
+ * number of mask pixels set (zeroed by the call).  No resize: the caller's slices are model-sized. */
+int ub2_predict_mask(const float* logits, int N, int C, long long HW, float threshold, unsigned char* mask,
+                     int* positives, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,6 +140,77 @@ def metrics_case(metrics_mod):
     return out
 
 
+def io_case():
+    """The per-slice host work either side of the model, through the reference's own functions:
+    apply_basic_transforms (unet/data/augmentations.py:117-170) on top of the two lines of
+    LungTumorDataset.__getitem__ that precede it (dataset.py:146-151), and preprocess_image /
+    postprocess_mask of scripts/predict.py (which reads a PNG: one is written to a temp dir)."""
+    import importlib.util
+    import tempfile
+    from pathlib import Path
+    from PIL import Image
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    aug = load("ref_augmentations", "unet/data/augmentations.py")
+    rng = np.random.default_rng(21)
+    n, h, w = 3, 48, 48
+    images = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    images[0, 0, :256 % w] = 0
+    images[0].reshape(-1)[:256] = np.arange(256, dtype=np.uint8)      # every grey level once
+    labels = (rng.random((n, h, w)) < 0.2).astype(np.uint8) * 255
+    labels[1].reshape(-1)[:4] = (127, 128, 1, 254)                      # the > 127 boundary
+    xs, ts, flags = [], [], []
+    for i in range(n):
+        image = np.array(Image.fromarray(images[i]).convert("L"), dtype=np.float32) / 255.0   # dataset.py:146
+        mask = (np.array(Image.fromarray(labels[i]).convert("L"), dtype=np.uint8) > 127).astype(np.int64)  # :147-151
+        # find a numpy seed whose first draw takes the branch wanted for this slice (flip for odd i)
+        want = i % 2 == 1
+        seed = next(s for s in range(100) if (np.random.RandomState(s).rand() > 0.5) == want)
+        np.random.seed(seed)
+        x, t = aug.apply_basic_transforms(image, mask, img_size=h, is_train=True)
+        xs.append(x); ts.append(t); flags.append(1 if want else 0)
+    x_ref, t_ref = torch.stack(xs), torch.stack(ts)
+    flags = np.array(flags, dtype=np.uint8)
+    ox, ot = O.prepare_slices(images, labels, flags)
+    assert torch.equal(ox, x_ref) and torch.equal(ot, t_ref), "oracle vs apply_basic_transforms"
+
+    sys.argv = ["predict.py"]
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "unet" or k.startswith("unet.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, REF)
+    try:
+        pred = load("ref_predict", "scripts/predict.py")
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == "unet" or k.startswith("unet.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
+    with tempfile.TemporaryDirectory() as d:
+        path = Path(d) / "slice.png"
+        Image.fromarray(images[0]).save(path)
+        tensor, _, size = pred.preprocess_image(path, img_size=h)
+    px, _ = O.prepare_slices(images[:1], requantize=False)
+    assert size == (w, h) and torch.equal(px, tensor), "oracle vs preprocess_image"
+
+    g = torch.Generator().manual_seed(22)
+    z = 3 * torch.randn(2, 2, h, w, generator=g)
+    masks, counts = [], []
+    for i in range(2):
+        m = pred.postprocess_mask(z[i:i + 1], (w, h), threshold=0.6)
+        masks.append(m); counts.append(int((m > 127).sum()))
+    om, oc = O.predict_mask(z, 0.6)
+    assert np.array_equal(om, np.stack(masks)) and list(oc) == counts, "oracle vs postprocess_mask"
+    return {"images": torch.from_numpy(images), "labels": torch.from_numpy(labels), "flags": torch.from_numpy(flags),
+            "x": x_ref, "t": t_ref, "x_predict": tensor, "z": z, "threshold": 0.6,
+            "mask": torch.from_numpy(np.stack(masks)), "positives": torch.tensor(counts)}
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -154,6 +225,7 @@ def main():
     torch.save(cases, os.path.join(OUT, "models.pt"))
     torch.save(loss_case(loss_mod), os.path.join(OUT, "loss.pt"))
     torch.save(metrics_case(metrics_mod), os.path.join(OUT, "metrics.pt"))
+    torch.save(io_case(), os.path.join(OUT, "io.pt"))
     # default-initialisation fingerprint: same seed -> same parameters as the reference constructor
     torch.manual_seed(42)
     ref = net.AttentionUNet(1, 2, True, 16)

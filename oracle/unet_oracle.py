@@ -349,6 +349,45 @@ def dice_per_class(pred: Tensor, target: Tensor, num_classes: int = 2, smooth: f
     return torch.stack(out)
 
 
+# ------------------------------------------------------------------------------- either side of the model
+def prepare_slices(images: np.ndarray, labels: Optional[np.ndarray] = None, flags: Optional[np.ndarray] = None,
+                   mean: float = 0.5, std: float = 0.5, requantize: bool = True):
+    """uint8 slices (N,H,W) -> (x fp32 (N,1,H,W), targets int64 (N,H,W) or None).
+
+    LungTumorDataset.__getitem__ (unet/data/dataset.py:146-151): image = float32(px) / 255.0,
+    mask = (label > 127) as int64; apply_basic_transforms (unet/data/augmentations.py:148-170):
+    the image goes through uint8 once more, ``(image * 255).astype(np.uint8)`` then / 255.0 again
+    (requantize), np.fliplr on both (flags bit 0; bit 1 = np.flipud, the albumentations pipeline's
+    VerticalFlip, augmentations.py:78), ``(image - mean) / std`` in float32.  requantize=False is
+    preprocess_image of scripts/predict.py:122-130 (one division, no flip)."""
+    images = np.asarray(images, dtype=np.uint8)
+    x = images.astype(np.float32) / 255.0
+    if requantize:
+        x = (x * 255).astype(np.uint8).astype(np.float32) / 255.0
+    t = None if labels is None else (np.asarray(labels, dtype=np.uint8) > 127).astype(np.int64)
+    if flags is not None:
+        x, t = x.copy(), (None if t is None else t.copy())
+        for n, f in enumerate(np.asarray(flags).reshape(-1)):
+            if f & 1:
+                x[n] = np.fliplr(x[n])
+                if t is not None:
+                    t[n] = np.fliplr(t[n])
+            if f & 2:
+                x[n] = np.flipud(x[n])
+                if t is not None:
+                    t[n] = np.flipud(t[n])
+    x = (x - np.float32(mean)) / np.float32(std)
+    return torch.from_numpy(np.ascontiguousarray(x)).unsqueeze(1).float(), (None if t is None else torch.from_numpy(t).long())
+
+
+def predict_mask(logits: Tensor, threshold: float = 0.5):
+    """postprocess_mask + tumor_ratio (scripts/predict.py:155-159, :238) per image: mask uint8 =
+    255 * (softmax(logits, 1)[:, 1] > threshold), positives = number of set pixels."""
+    prob = torch.softmax(logits.float(), dim=1)[:, 1].cpu().numpy()
+    mask = (prob > threshold).astype(np.uint8) * 255
+    return mask, (mask > 127).reshape(mask.shape[0], -1).sum(axis=1).astype(np.int64)
+
+
 # ------------------------------------------------------------------------------- train step
 def clone_state(sd):
     return {k: v.clone() for k, v in sd.items()}

@@ -103,3 +103,19 @@ def test_metrics_host_side():
         assert m.get_confusion_matrix().dtype == np.int64
         m.reset()
         assert m.confusion_matrix.sum() == 0
+
+
+def test_input_pipeline_host_side():
+    """Flip bits are reproducible from the seed, and the device pipeline refuses a CPU device."""
+    from unet.data import DeviceBatchPipeline
+    from unet.data.device import draw_flags, prepare_batch
+    a = draw_flags(64, torch.Generator().manual_seed(5), 0.5, 0.3)
+    b = draw_flags(64, torch.Generator().manual_seed(5), 0.5, 0.3)
+    assert a.dtype == torch.uint8 and torch.equal(a, b) and int(a.max()) <= 3
+    assert 10 < int((a & 1).sum()) < 54 and 3 < int((a >> 1).sum()) < 40
+    assert int(draw_flags(16, torch.Generator().manual_seed(1), 0.0, 0.0).sum()) == 0
+    assert int(draw_flags(16, torch.Generator().manual_seed(1), 1.0, 1.0).min()) == 3
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DeviceBatchPipeline([], "cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        prepare_batch(torch.zeros(1, 16, 16, dtype=torch.uint8))

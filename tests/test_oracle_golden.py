@@ -67,3 +67,18 @@ def test_state_dict_shapes_match_appendix_a():
     assert len(O.state_dict_shapes(attention=False)) == 110
     assert len(O.state_dict_shapes(deep_supervision=True)) == 188
     assert len(O.state_dict_shapes(bilinear=False)) == 190
+
+
+def test_io_cases():
+    """prepare_slices / predict_mask against apply_basic_transforms, preprocess_image and
+    postprocess_mask of the reference (fixture written by oracle/gen_golden.py:io_case)."""
+    g = _load("io.pt")
+    x, t = O.prepare_slices(g["images"].numpy(), g["labels"].numpy(), g["flags"].numpy())
+    assert torch.equal(x, g["x"]) and torch.equal(t, g["t"])
+    xp, none = O.prepare_slices(g["images"][:1].numpy(), requantize=False)
+    assert none is None and torch.equal(xp, g["x_predict"])
+    # the transform's second uint8 round trip changes no grey level
+    lv = np.arange(256, dtype=np.uint8).reshape(1, 16, 16)
+    assert torch.equal(O.prepare_slices(lv, requantize=True)[0], O.prepare_slices(lv, requantize=False)[0])
+    m, c = O.predict_mask(g["z"], g["threshold"])
+    assert np.array_equal(m, g["mask"].numpy()) and np.array_equal(c, g["positives"].numpy())

@@ -1,0 +1,219 @@
+// The two ends of the forward path: what a data-loader worker does to a slice
+// before the model sees it, and what predict.py does to the logits afterwards.
+//
+// Input side (unet/data/dataset.py:146-171 with the albumentations-free transform the reference
+// falls back to, unet/data/augmentations.py:117-170; scripts/predict.py:100-136):
+//   image  = uint8 PNG slice;  x = ((px / 255) - mean) / std  in fp32, shape (N,1,H,W)
+//   target = (label > 127) as int64, shape (N,H,W)
+//   training: horizontal flip of both (augmentations.py:160-162); a vertical flip bit is accepted
+//   as well (the albumentations pipeline has one, augmentations.py:78).
+// The reference does this per slice on the host and ships 12 B/pixel (fp32 image + int64 target)
+// over PCIe; here the uint8 slices are shipped (2 B/pixel) and expanded on the device, in one
+// pass bounded by the 12 B/pixel written to HBM.
+//
+// The fallback transform round-trips the image through uint8 again
+// (augmentations.py:148 `(image * 255).astype(np.uint8)` on `px / 255.0`); in float32 that is the
+// identity on all 256 grey levels (tests/test_oracle_golden.py checks it), so the dataset path and
+// predict.py's preprocess_image are the same map from a pixel value to one of 256 floats.  The table
+// is built per block in shared memory with IEEE division / subtraction (no FMA contraction), so the
+// result equals numpy's bit for bit.
+//
+// Output side (scripts/predict.py:138-166, 232-240): mask = (softmax(logits)[1] > thr) * 255 as
+// uint8 and tumor_ratio = #(mask > 127) / pixels, per image, without the logits leaving the GPU.
+#include "../../include/unetb200.h"
+#include "conv.h"
+#include "ptx.cuh"
+#include "vec.cuh"
+
+namespace ub2 {
+
+static constexpr int kIoThreads = 256;
+
+__device__ __forceinline__ uint32_t byte_reverse(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+// ((px / 255) - mean) / std, each operation rounded once as numpy's float32 arithmetic does
+__device__ __forceinline__ float normalised_level(int px, float mean, float stdv) {
+  return __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(px), 255.f), mean), stdv);
+}
+
+// One item = 4 consecutive pixels of a row (W % 4 == 0): a 32-bit load per plane, one 128-bit store
+// of the image and one 256-bit store of the target, so that a warp writes 512 + 1024 contiguous
+// bytes per item row.  Four items per thread are in flight together.
+__global__ void __launch_bounds__(kIoThreads)
+prepare_batch_kernel(const unsigned char* __restrict__ img, const unsigned char* __restrict__ label,
+                     const unsigned char* __restrict__ flags, int N, int H, int W, float mean, float stdv,
+                     float* __restrict__ x, long long* __restrict__ t) {
+  __shared__ float s_lut[256];
+  s_lut[threadIdx.x] = normalised_level(threadIdx.x, mean, stdv);
+  __syncthreads();
+  constexpr int U = 4;
+  const unsigned wq = static_cast<unsigned>(W) >> 2, uh = static_cast<unsigned>(H);
+  const unsigned total = static_cast<unsigned>(N) * uh * wq;   // < 2^30 (checked by the launcher)
+  const unsigned stride = gridDim.x * kIoThreads;
+  for (unsigned i0 = blockIdx.x * kIoThreads + threadIdx.x; i0 < total; i0 += U * stride) {
+    uint32_t a[U], b[U];
+    bool flip[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned i = i0 + u * stride;
+      a[u] = b[u] = 0u;
+      flip[u] = false;
+      if (i < total) {
+        const unsigned xq = i % wq, row = i / wq;
+        const unsigned y = row % uh, n = row / uh;
+        const unsigned f = flags != nullptr ? __ldg(flags + n) : 0u;
+        const unsigned sy = (f & 2u) ? uh - 1u - y : y;
+        const unsigned sxq = (f & 1u) ? wq - 1u - xq : xq;
+        const size_t src = (static_cast<size_t>(n) * uh + sy) * W + (sxq << 2);
+        flip[u] = (f & 1u) != 0u;
+        a[u] = __ldg(reinterpret_cast<const uint32_t*>(img + src));
+        if (label != nullptr) b[u] = __ldg(reinterpret_cast<const uint32_t*>(label + src));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = static_cast<size_t>(i0) + static_cast<size_t>(u) * stride;
+      if (i >= total) break;
+      const uint32_t av = flip[u] ? byte_reverse(a[u]) : a[u];
+      float4 o;
+      o.x = s_lut[av & 0xffu];
+      o.y = s_lut[(av >> 8) & 0xffu];
+      o.z = s_lut[(av >> 16) & 0xffu];
+      o.w = s_lut[av >> 24];
+      __stcs(reinterpret_cast<float4*>(x) + i, o);
+      if (label != nullptr) {
+        const uint32_t bv = flip[u] ? byte_reverse(b[u]) : b[u];
+        // int64 0/1 per pixel: low word = label > 127, high word = 0
+        const uint4 lo = make_uint4((bv >> 7) & 1u, 0u, (bv >> 15) & 1u, 0u);
+        const uint4 hi = make_uint4((bv >> 23) & 1u, 0u, bv >> 31, 0u);
+        st_global_256(t + 4 * i, lo, hi);
+      }
+    }
+  }
+}
+
+// Any width: one thread per pixel.
+__global__ void __launch_bounds__(kIoThreads)
+prepare_batch_scalar_kernel(const unsigned char* __restrict__ img, const unsigned char* __restrict__ label,
+                            const unsigned char* __restrict__ flags, int N, int H, int W, float mean,
+                            float stdv, float* __restrict__ x, long long* __restrict__ t) {
+  __shared__ float s_lut[256];
+  s_lut[threadIdx.x] = normalised_level(threadIdx.x, mean, stdv);
+  __syncthreads();
+  const long long total = static_cast<long long>(N) * H * W;
+  for (long long i = static_cast<long long>(blockIdx.x) * kIoThreads + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kIoThreads) {
+    const int xx = static_cast<int>(i % W);
+    const long long row = i / W;
+    const int y = static_cast<int>(row % H);
+    const int n = static_cast<int>(row / H);
+    const int f = flags != nullptr ? flags[n] : 0;
+    const int sy = (f & 2) ? H - 1 - y : y;
+    const int sx = (f & 1) ? W - 1 - xx : xx;
+    const long long src = (static_cast<long long>(n) * H + sy) * W + sx;
+    x[i] = s_lut[__ldg(img + src)];
+    if (label != nullptr) t[i] = __ldg(label + src) > 127 ? 1 : 0;
+  }
+}
+
+// softmax(dim=1)[1] as F.softmax forms it, exp(z - max) / sum (predict.py:155-159).  The larger
+// logit's term is exp(0) = 1 exactly, so one exponential gives the same bits as two.
+__device__ __forceinline__ float tumour_probability(float z0, float z1) {
+  const float e = expf(-fabsf(z1 - z0));
+  const float sum = 1.f + e;
+  return (z1 >= z0 ? 1.f : e) / sum;
+}
+
+// One block per (image, chunk of pixels): 4 pixels per thread per iteration.
+__global__ void __launch_bounds__(kIoThreads)
+predict_mask_kernel(const float* __restrict__ logits, long long HW, int chunks_per_image, float threshold,
+                    unsigned char* __restrict__ mask, int* __restrict__ positives) {
+  __shared__ int s_warp[kIoThreads / 32];
+  const int n = blockIdx.x / chunks_per_image, chunk = blockIdx.x % chunks_per_image;
+  const float* z0 = logits + static_cast<long long>(n) * 2 * HW;
+  const float* z1 = z0 + HW;
+  unsigned char* m = mask + static_cast<long long>(n) * HW;
+  const long long per = (((HW + 3) / 4 + chunks_per_image - 1) / chunks_per_image) * 4;
+  const long long begin = per * chunk;
+  long long end = begin + per;
+  if (end > HW) end = HW;
+  int count = 0;
+  const bool vec = (HW & 3) == 0;
+  if (vec) {
+    for (long long i = begin + threadIdx.x * 4LL; i < end; i += kIoThreads * 4LL) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(z0 + i));
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(z1 + i));
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      uint32_t out = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool on = tumour_probability(av[k], bv[k]) > threshold;
+        count += on;
+        out |= on ? (0xffu << (8 * k)) : 0u;
+      }
+      *reinterpret_cast<uint32_t*>(m + i) = out;
+    }
+  } else {
+    for (long long i = begin + threadIdx.x; i < end; i += kIoThreads) {
+      const bool on = tumour_probability(z0[i], z1[i]) > threshold;
+      count += on;
+      m[i] = on ? 255 : 0;
+    }
+  }
+  count = __reduce_add_sync(0xffffffffu, count);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = count;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < kIoThreads / 32; ++w) tot += s_warp[w];
+    if (tot != 0) atomicAdd(positives + n, tot);   // integer: order independent
+  }
+}
+
+}  // namespace ub2
+
+using namespace ub2;
+
+extern "C" {
+
+int ub2_prepare_batch(const unsigned char* images, const unsigned char* labels, const unsigned char* flags,
+                      int N, int H, int W, float mean, float std, float* x, long long* targets,
+                      void* stream) {
+  if (N <= 0 || H <= 0 || W <= 0 || images == nullptr || x == nullptr) return UB2_ERR_SHAPE;
+  if ((labels == nullptr) != (targets == nullptr)) return UB2_ERR_SHAPE;
+  if (!(std != 0.f)) return UB2_ERR_SHAPE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool vec = (W % 4 == 0) && static_cast<long long>(N) * H * (W / 4) < (1LL << 30) && ((reinterpret_cast<uintptr_t>(images) | reinterpret_cast<uintptr_t>(labels)) & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(targets) & 31) == 0;
+  if (vec) {
+    const long long items = (static_cast<long long>(N) * H * (W / 4) + 3) / 4;   // 4 items per thread
+    prepare_batch_kernel<<<stream_grid(items, kIoThreads, num_sms(), 8), kIoThreads, 0, s>>>(
+        images, labels, flags, N, H, W, mean, std, x, targets);
+  } else {
+    const long long items = static_cast<long long>(N) * H * W;
+    prepare_batch_scalar_kernel<<<stream_grid(items, kIoThreads, num_sms(), 8), kIoThreads, 0, s>>>(
+        images, labels, flags, N, H, W, mean, std, x, targets);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_predict_mask(const float* logits, int N, int C, long long HW, float threshold, unsigned char* mask,
+                     int* positives, void* stream) {
+  if (N <= 0 || HW <= 0 || logits == nullptr || mask == nullptr || positives == nullptr) return UB2_ERR_SHAPE;
+  if (C != 2) return UB2_ERR_SHAPE;   // predict.py:157 reads the tumour class of a 2-class softmax
+  if (HW >= (1LL << 31)) return UB2_ERR_SHAPE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(positives, 0, sizeof(int) * N, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  // enough blocks to fill the machine a few times over, at least 4096 pixels each
+  long long chunks = (static_cast<long long>(num_sms()) * 8 + N - 1) / N;
+  const long long max_chunks = (HW + 4095) / 4096;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  predict_mask_kernel<<<static_cast<unsigned>(N * chunks), kIoThreads, 0, s>>>(logits, HW, static_cast<int>(chunks),
+                                                                               threshold, mask, positives);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

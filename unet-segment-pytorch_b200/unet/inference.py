@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import torch
 
+from . import kernels as K
 from . import ops
 from .kernels import WeightPacker
 
@@ -78,3 +79,25 @@ class InferenceEngine:
         gx.copy_(x, non_blocking=True)
         graph.replay()
         return gout
+
+    @torch.no_grad()
+    def predict(self, x: torch.Tensor, threshold: float = 0.5, mean: float = 0.5, std: float = 0.5):
+        """``predict_single`` (scripts/predict.py:204-240) for a batch, without leaving the GPU.
+
+        ``x``: normalised fp32 ``(N,1,H,W)`` (``preprocess_image``'s tensor) or raw uint8 slices
+        ``(N,H,W)`` / ``(N,1,H,W)``, which are normalised on the device as ``preprocess_image``
+        (predict.py:126-127) does.  Returns ``(mask, tumor_ratio)``: ``mask`` uint8 ``(N,H,W)`` with
+        255 where ``softmax(logits)[1] > threshold`` (``postprocess_mask``, predict.py:155-159) and
+        ``tumor_ratio`` fp64 ``(N)`` = set pixels / pixels (predict.py:238).  Both are device tensors;
+        nothing synchronises."""
+        dev = next(self.model.parameters()).device
+        x = x.to(dev, non_blocking=True)
+        if x.dtype == torch.uint8:
+            if x.dim() == 4:
+                x = x[:, 0]
+            x, _ = K.prepare_batch(x.contiguous(), None, None, mean, std)
+        logits = self(x)
+        if isinstance(logits, (list, tuple)):
+            logits = logits[0]
+        mask, positives = K.predict_mask(logits.contiguous(), threshold)
+        return mask, positives.to(torch.float64) / float(mask.shape[1] * mask.shape[2])

@@ -482,3 +482,41 @@ def confusion(pred, target, num_classes, cm, ignore_index=None, threshold=None, 
             int(ignore_index is not None), c_float(threshold if threshold is not None else 0.5), ptr(cm),
             ptr(mask_out), stream())
     return cm
+
+
+# --------------------------------------------------------------------------- either side of the forward
+def prepare_batch(images, labels=None, flags=None, mean=0.5, std=0.5, x=None, targets=None):
+    """uint8 slices (N,H,W) -> x fp32 (N,1,H,W) = ((px/255)-mean)/std and targets int64 (N,H,W) =
+    label > 127, optionally flipped per image (flags uint8 (N): bit 0 horizontal, bit 1 vertical)."""
+    assert images.dtype == torch.uint8 and images.dim() == 3 and images.is_contiguous()
+    n, h, w = images.shape
+    if x is None:
+        x = torch.empty((n, 1, h, w), device=images.device, dtype=F32)
+    assert x.dtype == F32 and x.is_contiguous() and x.numel() == n * h * w
+    if labels is not None:
+        assert labels.dtype == torch.uint8 and labels.shape == images.shape and labels.is_contiguous()
+        if targets is None:
+            targets = torch.empty((n, h, w), device=images.device, dtype=torch.int64)
+        assert targets.dtype == torch.int64 and targets.is_contiguous() and targets.numel() == n * h * w
+    else:
+        targets = None
+    if flags is not None:
+        assert flags.dtype == torch.uint8 and flags.numel() == n and flags.is_contiguous()
+    _C.call("ub2_prepare_batch", ptr(images), ptr(labels), ptr(flags), n, h, w, c_float(mean), c_float(std),
+            ptr(x), ptr(targets), stream())
+    return x, targets
+
+
+def predict_mask(logits, threshold=0.5, mask=None, positives=None):
+    """logits fp32 (N,2,H,W) -> (mask uint8 (N,H,W) in {0,255}, positives int32 (N))."""
+    assert logits.dim() == 4 and logits.dtype == F32 and logits.is_contiguous()
+    n, c, h, w = logits.shape
+    if mask is None:
+        mask = torch.empty((n, h, w), device=logits.device, dtype=torch.uint8)
+    if positives is None:
+        positives = torch.empty((n,), device=logits.device, dtype=torch.int32)
+    assert mask.dtype == torch.uint8 and mask.is_contiguous() and mask.numel() == n * h * w
+    assert positives.dtype == torch.int32 and positives.numel() == n
+    _C.call("ub2_predict_mask", ptr(logits), n, c, c_longlong(h * w), c_float(threshold), ptr(mask), ptr(positives),
+            stream())
+    return mask, positives
