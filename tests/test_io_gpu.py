@@ -131,7 +131,8 @@ def test_pipeline_feeds_trainer_and_engine_predicts():
     raw = batches[0][0].cuda()
     mask, ratio = engine.predict(raw, threshold=0.4)
     x, _ = K.prepare_batch(raw)
-    logits = model.eval()(x)
+    with torch.no_grad():
+        logits = model.eval()(x)
     ref_mask, ref_pos = K.predict_mask(logits.contiguous(), 0.4)
     assert torch.equal(mask, ref_mask)
     assert torch.allclose(ratio, ref_pos.double() / (64 * 64))

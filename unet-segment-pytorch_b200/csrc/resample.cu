@@ -312,15 +312,18 @@ static bool bwd_tiled_ok(const UpGeom& g) {
 // to the two source rows it lies between, which are kept in registers and written when the walk has
 // passed them.  ~220 instructions per 16-byte output instead of ~1000 for the gather kernels (both
 // were issue bound), deterministic, no shared memory.
+// Strip length: 16 rows when that still fills the machine; shorter strips (more, shorter walks: a
+// thread's walk is a chain of dependent load latencies, ~1.8 us per destination row) when the batch
+// is small — at batch 4 every level has fewer threads than one wave even with 16-row strips.
 static constexpr int kBwdStrip = 16;
 
 __global__ void __launch_bounds__(256)
 upsample_bwd_strip_kernel(const __nv_bfloat16* __restrict__ dout, int ld_dout, __nv_bfloat16* __restrict__ din,
-                          int ld_din, int accumulate, UpGeom g) {
+                          int ld_din, int accumulate, int strip, UpGeom g) {
   const int j = blockIdx.x * blockDim.y + threadIdx.y;   // source column
   const int n = blockIdx.z;
   if (j >= g.win) return;
-  const int ia = blockIdx.y * kBwdStrip, ib = min(ia + kBwdStrip, g.hin);
+  const int ia = blockIdx.y * strip, ib = min(ia + strip, g.hin);
   // column taps: destination columns v0 .. v0+4 (see upsample_bwd_tiled_kernel)
   const float fj = static_cast<float>(j);
   int v0 = static_cast<int>(floorf((fj - 1.f) / g.rw)) + 1;
@@ -453,9 +456,13 @@ int ub2_upsample_bwd(const void* dout, int ld_dout, void* din, int ld_din, int a
   UpGeom g = up_geom(N, hin, win, hu, wu, Ho, Wo, C);
   if (bwd_strip_ok(g)) {
     const dim3 sblock = up_block(g.cgs);
-    const dim3 sgrid((win + sblock.y - 1) / sblock.y, (hin + kBwdStrip - 1) / kBwdStrip, N);
+    const long long wave = static_cast<long long>(num_sms()) * 2048;
+    int strip = kBwdStrip;
+    while (strip > 2 && static_cast<long long>(N) * ((hin + strip - 1) / strip) * win * g.cgs < wave) strip >>= 1;
+    const dim3 sgrid((win + sblock.y - 1) / sblock.y, (hin + strip - 1) / strip, N);
     upsample_bwd_strip_kernel<<<sgrid, sblock, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din, accumulate, g);
+        static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din, accumulate,
+        strip, g);
     return static_cast<int>(cudaGetLastError());
   }
   if (bwd_tiled_ok(g)) {
