@@ -229,6 +229,82 @@ conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
   }
 }
 
+// Cin == 1, W % 4 == 0: an item is 4 consecutive pixels x 8 channels (as conv_in_fwd4): four
+// 128-bit dy loads in flight (the next item's are issued before this item's 288 FMAs), the 3x6
+// input window shared by the 4 pixels, no per-pixel index arithmetic.
+__global__ void __launch_bounds__(kHeadThreads, 2)
+conv_in_wgrad4_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int ld_dy,
+                      double* partials, int N, int H, int W, int Cout) {
+  extern __shared__ float s_red[];  // [lanes][cgs][8]
+  const int cgs = Cout / 8;
+  const int lanes = blockDim.x / cgs;
+  const int lane = threadIdx.x / cgs, cg = threadIdx.x % cgs;
+  const bool active = lane < lanes;
+  const unsigned wq4 = static_cast<unsigned>(W) >> 2;
+  const unsigned items = static_cast<unsigned>(N) * H * wq4;
+  const unsigned stride = gridDim.x * lanes;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  if (active) {
+    unsigned item = blockIdx.x * lanes + lane;
+    uint4 d[4];
+    auto load_dy = [&](unsigned it) {
+      const __nv_bfloat16* p = dy + static_cast<size_t>(it) * 4 * ld_dy + cg * 8;
+#pragma unroll
+      for (int px = 0; px < 4; ++px) d[px] = ld_stream16(p + static_cast<size_t>(px) * ld_dy);
+    };
+    if (item < items) load_dy(item);
+    for (; item < items; item += stride) {
+      const unsigned row = item / wq4;
+      const int wq = static_cast<int>(item - row * wq4) << 2;
+      const int hq = static_cast<int>(row % static_cast<unsigned>(H));
+      const float* xrow = x + static_cast<size_t>(row) * W;
+      float xv[3][6];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = hq + r - 1;
+        const bool rv = hh >= 0 && hh < H;
+        const float* xp = xrow + (r - 1) * W + wq;
+        xv[r][0] = (rv && wq > 0) ? __ldg(xp - 1) : 0.f;
+        const float4 mid = rv ? __ldg(reinterpret_cast<const float4*>(xp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[r][1] = mid.x; xv[r][2] = mid.y; xv[r][3] = mid.z; xv[r][4] = mid.w;
+        xv[r][5] = (rv && wq + 4 < W) ? __ldg(xp + 4) : 0.f;
+      }
+      F8 cur[4];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) cur[px] = unpack8(d[px]);
+      if (item + stride < items) load_dy(item + stride);
+#pragma unroll
+      for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int sft = 0; sft < 3; ++sft)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[r * 3 + sft][k] = fmaf(xv[r][px + sft], cur[px].v[k], acc[r * 3 + sft][k]);
+    }
+  }
+  double* rowp = partials + static_cast<size_t>(blockIdx.x) * 9 * Cout;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    float* mine = s_red + (static_cast<size_t>(lane) * cgs + cg) * 8;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mine[k] = acc[t][k];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cgs * 8; idx += blockDim.x) {
+      double a = 0.0;
+      for (int l = 0; l < lanes; ++l) a += static_cast<double>(s_red[static_cast<size_t>(l) * cgs * 8 + idx]);
+      rowp[t * Cout + idx] = a;
+    }
+    __syncthreads();
+  }
+}
+
 // grad[co][ci][t] += sum_rows partials[row][ci][t][co];  blockDim = (32, 32)
 __global__ void conv_in_wgrad_finalize_kernel(const double* __restrict__ partials, int rows, int Cin,
                                               int Cout, float* grad) {
@@ -333,37 +409,69 @@ outc_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ 
       for (int i = 0; i < 8; ++i) accw[gi][k][i] = 0.f;
 #pragma unroll
   for (int k = 0; k < kMaxClasses; ++k) accb[k] = 0.f;
-  for (int base = static_cast<int>(blockIdx.x) * g.slots; base < g.pixels;
-       base += static_cast<int>(gridDim.x) * g.slots) {
-    const int pix = base + slot;
-    if (pix >= g.pixels) continue;
-    const int n = pix / g.HW, r = pix % g.HW;
-    float d[kMaxClasses];
+  // U pixels per trip (their loads are issued together); with few classes the weights stay in registers
+  constexpr int U = (G == 1 && KMAX <= 2) ? 4 : ((G == 1 && KMAX <= 4) ? 2 : 1);
+  constexpr bool kHoist = G * KMAX <= 4;
+  F8 wreg[kHoist ? G : 1][kHoist ? KMAX : 1];
+  if (kHoist) {
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
-      d[k] = (k < g.K) ? __ldg(dl + (n * g.K + k) * g.HW + r) : 0.f;
-      if (j == 0) accb[k] += d[k];
+    for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k) {
+        const int cg = j + gi * g.tpp;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          wreg[kHoist ? gi : 0][kHoist ? k : 0].v[i] =
+              (k < g.K && cg < g.cgs) ? __ldg(w + static_cast<size_t>(k) * g.C + cg * 8 + i) : 0.f;
+      }
+  }
+  const int stride = static_cast<int>(gridDim.x) * g.slots;
+  for (int base = static_cast<int>(blockIdx.x) * g.slots; base < g.pixels; base += U * stride) {
+    float d[U][kMaxClasses];
+    uint4 v[U][G];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * stride + slot;
+      const bool pv = pix < g.pixels;
+      const int n = pv ? pix / g.HW : 0, r = pv ? pix % g.HW : 0;
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k) d[u][k] = (pv && k < g.K) ? __ldg(dl + (n * g.K + k) * g.HW + r) : 0.f;
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) {
+        const int cg = j + gi * g.tpp;
+        v[u][gi] = (pv && cg < g.cgs) ? ld_stream16(a + static_cast<size_t>(pix) * ld_a + cg * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
     }
 #pragma unroll
-    for (int gi = 0; gi < G; ++gi) {
-      const int cg = j + gi * g.tpp;
-      if (cg < g.cgs) {
-        const F8 v = load8_stream(a + static_cast<size_t>(pix) * ld_a + cg * 8);
-        F8 o;
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * stride + slot;
+      if (pix >= g.pixels) continue;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+      for (int k = 0; k < kMaxClasses; ++k)
+        if (j == 0) accb[k] += d[u][k];
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) {
-          if (k < g.K) {
-            const F8 wv = loadf8(w + static_cast<size_t>(k) * g.C + cg * 8);
+      for (int gi = 0; gi < G; ++gi) {
+        const int cg = j + gi * g.tpp;
+        if (cg < g.cgs) {
+          const F8 vv = unpack8(v[u][gi]);
+          F8 o;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              o.v[i] = fmaf(d[k], wv.v[i], o.v[i]);
-              accw[gi][k][i] = fmaf(d[k], v.v[i], accw[gi][k][i]);
+          for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+#pragma unroll
+          for (int k = 0; k < kMaxClasses; ++k) {
+            if (k < g.K) {
+              F8 wv;
+              if (kHoist) wv = wreg[kHoist ? gi : 0][kHoist ? k : 0];
+              else wv = loadf8(w + static_cast<size_t>(k) * g.C + cg * 8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                o.v[i] = fmaf(d[u][k], wv.v[i], o.v[i]);
+                accw[gi][k][i] = fmaf(d[u][k], vv.v[i], accw[gi][k][i]);
+              }
             }
           }
+          if (da != nullptr) store8(da + static_cast<size_t>(pix) * ld_da + cg * 8, o);
         }
-        if (da != nullptr) store8(da + static_cast<size_t>(pix) * ld_da + cg * 8, o);
       }
     }
   }
@@ -478,8 +586,13 @@ int ub2_conv_in_wgrad(const float* x, const void* dy, int ld_dy, double* partial
   if (grid != rows) return UB2_ERR_WORKSPACE;
   const size_t smem = static_cast<size_t>(lanes) * cgs * 8 * sizeof(float);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  conv_in_wgrad_kernel<<<dim3(grid, Cin), block, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dy),
-                                                           ld_dy, partials, N, Cin, H, W, Cout);
+  if (Cin == 1 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      static_cast<double>(N) * H * W < 4.0e9)
+    conv_in_wgrad4_kernel<<<grid, block, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dy), ld_dy, partials, N,
+                                                    H, W, Cout);
+  else
+    conv_in_wgrad_kernel<<<dim3(grid, Cin), block, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dy),
+                                                             ld_dy, partials, N, Cin, H, W, Cout);
   const int total = Cout * Cin * 9;
   conv_in_wgrad_finalize_kernel<<<(total + 31) / 32, dim3(32, 32), 0, s>>>(partials, grid, Cin, Cout, grad);
   return static_cast<int>(cudaGetLastError());
