@@ -10,7 +10,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "unet-segment-pytorch_b200"))
 sys.path.insert(0, ROOT)
-from oracle import unet_oracle as O  # noqa: E402  (synthetic inputs only)
+from bench import synthetic_batch  # noqa: E402  (the bench's own generator; oracle/ is for tests only)
 from unet.inference import InferenceEngine  # noqa: E402
 from unet.models import AttentionUNet, UNet  # noqa: E402
 from unet.optim import FusedAdamW  # noqa: E402
@@ -40,7 +40,7 @@ if "cfg3" in which:
     model = UNet(1, 2, True, 64).to(dev)
     tr = BatchShardedTrainer(model, DiceBCELoss(), FusedAdamW(model.parameters(), lr=5e-5, weight_decay=1e-4),
                              grad_clip=1.0, cuda_graph=True)
-    x, t = O.synthetic_batch(32, 512, 512, seed=1)
+    x, t = synthetic_batch(32, 512, 512, seed=1)
     x, t = x.to(dev), t.to(dev)
     ms = timed(lambda: tr.step(x, t), 10, 8)
     flops = 32 * 957_509_271_552
@@ -53,7 +53,7 @@ if "cfg5" in which:
     model = AttentionUNet(1, 2, True, 64).to(dev).eval()
     metrics = SegmentationMetrics(2)
     for b in (1, 2, 4, 8, 16, 32, 64, 128, 256):
-        x, t = O.synthetic_batch(min(b, 32), 512, 512, seed=2)
+        x, t = synthetic_batch(min(b, 32), 512, 512, seed=2)
         reps = (b + x.shape[0] - 1) // x.shape[0]
         x = x.repeat(reps, 1, 1, 1)[:b].to(dev)
         t = t.repeat(reps, 1, 1)[:b].to(dev)

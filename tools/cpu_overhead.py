@@ -4,7 +4,7 @@ import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "unet-segment-pytorch_b200")); sys.path.insert(0, ROOT)
-from oracle import unet_oracle as O
+from bench import synthetic_batch  # noqa: E402  (the bench's own generator; oracle/ is for tests only)
 from unet.models import AttentionUNet
 from unet.parallel import BatchShardedTrainer
 from unet.utils.loss import DiceBCELoss
@@ -15,7 +15,7 @@ model = AttentionUNet().to(dev)
 opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=1e-4, foreach=True)
 tr = BatchShardedTrainer(model, DiceBCELoss(), opt, grad_clip=1.0)
 for n, hw in ((1, 64), (4, 512)):
-    x, t = O.synthetic_batch(n, hw, hw, seed=1)
+    x, t = synthetic_batch(n, hw, hw, seed=1)
     x, t = x.to(dev), t.to(dev)
     for _ in range(5):
         tr.step(x, t)

@@ -13,7 +13,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "unet-segment-pytorch_b200"))
 sys.path.insert(0, ROOT)
-from oracle import unet_oracle as O  # noqa: E402  (synthetic inputs only)
+from bench import synthetic_batch  # noqa: E402  (the bench's own generator; oracle/ is for tests only)
 from unet import _C  # noqa: E402
 from unet.models import AttentionUNet, UNet  # noqa: E402
 from unet.parallel import BatchShardedTrainer  # noqa: E402
@@ -34,7 +34,7 @@ def main():
     from unet.optim import FusedAdamW
     opt = FusedAdamW(model.parameters(), lr=5e-5, weight_decay=1e-4)
     tr = BatchShardedTrainer(model, DiceBCELoss(), opt, grad_clip=1.0)
-    x, t = O.synthetic_batch(args.batch, 512, 512, seed=1234)
+    x, t = synthetic_batch(args.batch, 512, 512, seed=1234)
     x, t = x.to(dev), t.to(dev)
     for _ in range(3):
         tr.step(x, t)

@@ -45,6 +45,39 @@ __device__ __forceinline__ void pack_tile(const float* __restrict__ w, __nv_bflo
     if (col < nco) tile[col][j] = __float2bfloat16_rn(v[k]);
   }
   __syncthreads();
+  if (FULL) {
+    // 16-byte stores: a chunk is 8 consecutive bf16 of one output row (2 chunks per row of 16)
+    constexpr int kChunks = kPackT * TAPS * 2;
+    if (fwd != nullptr) {
+      for (int c = tid; c < kChunks; c += 256) {
+        const int half = c & 1, t = (c >> 1) % TAPS, col = (c >> 1) / TAPS;
+        uint32_t r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat16 lo = tile[col][(half * 8 + 2 * i) * TAPS + t];
+          const __nv_bfloat16 hi = tile[col][(half * 8 + 2 * i + 1) * TAPS + t];
+          r[i] = static_cast<uint32_t>(__bfloat16_as_ushort(lo)) | (static_cast<uint32_t>(__bfloat16_as_ushort(hi)) << 16);
+        }
+        *reinterpret_cast<uint4*>(fwd + (static_cast<size_t>(co0 + col) * TAPS + t) * Cin + ci0 + half * 8) =
+            make_uint4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    if (dgrad != nullptr) {
+      for (int c = tid; c < kChunks; c += 256) {
+        const int half = c & 1, t = (c >> 1) % TAPS, cil = (c >> 1) / TAPS;
+        uint32_t r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const __nv_bfloat16 lo = tile[half * 8 + 2 * i][cil * TAPS + t];
+          const __nv_bfloat16 hi = tile[half * 8 + 2 * i + 1][cil * TAPS + t];
+          r[i] = static_cast<uint32_t>(__bfloat16_as_ushort(lo)) | (static_cast<uint32_t>(__bfloat16_as_ushort(hi)) << 16);
+        }
+        *reinterpret_cast<uint4*>(dgrad + (static_cast<size_t>(ci0 + cil) * TAPS + (TAPS - 1 - t)) * Cout + co0 + half * 8) =
+            make_uint4(r[0], r[1], r[2], r[3]);
+      }
+    }
+    return;
+  }
   if (fwd != nullptr) {
 #pragma unroll
     for (int k = 0; k < TAPS; ++k) {
