@@ -53,3 +53,66 @@ def test_two_ranks_equal_accumulation(tmp_path):
         opt.step()
     for a, b in zip(got["params"], model.parameters()):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+def _accum_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unet.parallel import BatchShardedTrainer
+    model = _model()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    tr = BatchShardedTrainer(model, nn.CrossEntropyLoss(), opt, grad_clip=1.0, bucket_mb=0.00002,
+                             accumulation_steps=2)
+    before = [p.detach().clone() for p in model.parameters()]
+    for step in range(2):
+        for micro in range(2):
+            x, t = _data(2 * micro + rank)        # micro-batch index in the reference's loop order
+            tr.step(x, t)
+            if step == 0 and micro == 0:          # no optimizer step after the first micro-batch
+                assert all(torch.equal(a, b) for a, b in zip(before, model.parameters()))
+    if rank == 0:
+        torch.save([p.detach().clone() for p in model.parameters()], out)
+    dist.destroy_process_group()
+
+
+def _reference_loop(accum, steps):
+    model = _model()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    crit = nn.CrossEntropyLoss()
+    model.train()
+    for _ in range(steps):
+        opt.zero_grad()
+        for m in range(accum):
+            x, t = _data(m)
+            (crit(model(x), t) / accum).backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+    return model
+
+
+def test_two_ranks_times_two_local_micro_batches(tmp_path):
+    """2 ranks x accumulation_steps 2 == the reference loop with accumulation_steps 4 (train.py:127-147).
+    BatchNorm's running statistics see the micro-batches in a different order per rank, the
+    parameters do not depend on them."""
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_accum_worker, args=(2, 29613, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    ref = _reference_loop(4, 2)
+    for a, b in zip(got, ref.parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_single_process_accumulation():
+    from unet.parallel import BatchShardedTrainer
+    model = _model()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    tr = BatchShardedTrainer(model, nn.CrossEntropyLoss(), opt, grad_clip=1.0, accumulation_steps=3)
+    for _ in range(2):
+        for m in range(3):
+            loss = tr.step(*_data(m))
+            assert loss.dim() == 0
+    ref = _reference_loop(3, 2)
+    for a, b in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    for (k, a), (_, b) in zip(model.state_dict().items(), ref.state_dict().items()):
+        assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-6), k   # incl. running stats

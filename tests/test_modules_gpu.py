@@ -287,6 +287,51 @@ def test_cuda_graph_step_equals_eager():
         assert torch.equal(a, b)
 
 
+def test_accumulation_steps_graph_equals_eager_and_autograd():
+    """accumulation_steps=2 (train.py:127-147 on one GPU): replayed graphs (one per micro-batch phase)
+    == eager, and the accumulated gradient equals plain autograd's sum over the two micro-batches."""
+    from unet.models import AttentionUNet
+    from unet.optim import FusedAdamW
+    from unet.parallel import BatchShardedTrainer
+    from unet.utils.loss import DiceBCELoss
+    data = [tuple(v.cuda() for v in O.synthetic_batch(2, 64, 64, seed=20 + i, fg_fraction=0.05)) for i in range(2)]
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(3)
+        model = AttentionUNet(1, 2, True, 32).cuda()
+        start = [p.detach().clone() for p in model.parameters()]
+        opt = FusedAdamW(model.parameters(), lr=1e-3)
+        tr = BatchShardedTrainer(model, DiceBCELoss(), opt, grad_clip=1.0, cuda_graph=use_graph, graph_warmup=1,
+                                 accumulation_steps=2)
+        losses = []
+        for step in range(4):
+            for m in range(2):
+                losses.append(tr.step(*data[m]).item())
+                if step == 0 and m == 0:   # nothing moves before the second micro-batch
+                    assert all(torch.equal(a, b) for a, b in zip(start, model.parameters()))
+        results.append((losses, [p.detach().clone() for p in model.parameters()],
+                        int(model.inc.double_conv[1].num_batches_tracked)))
+    (l0, p0, n0), (l1, p1, n1) = results
+    assert n0 == n1 == 8
+    assert all(abs(a - b) <= 1e-6 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert torch.equal(a, b)
+    # gradient of one accumulated step against autograd's own accumulation (no sink, no buckets)
+    torch.manual_seed(3)
+    ref = AttentionUNet(1, 2, True, 32).cuda()
+    crit = DiceBCELoss()
+    ref.train()
+    for m in range(2):
+        (crit(ref(data[m][0]), data[m][1]) / 2).backward()
+    torch.manual_seed(3)
+    model = AttentionUNet(1, 2, True, 32).cuda()
+    tr = BatchShardedTrainer(model, crit, FusedAdamW(model.parameters(), lr=0.0, weight_decay=0.0), accumulation_steps=2)
+    for m in range(2):
+        tr.step(*data[m])
+    for (k, a), b in zip(model.named_parameters(), ref.parameters()):
+        assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-6 * float(b.grad.abs().max()) + 1e-9), k
+
+
 def test_direct_gradient_sink_equals_autograd():
     """With a gradient sink installed the kernels accumulate straight into param.grad and autograd
     sees None: the result is bit-identical to the AccumulateGrad path, every parameter reported once."""

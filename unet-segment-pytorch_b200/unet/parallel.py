@@ -56,11 +56,21 @@ class BatchShardedTrainer:
     grad_clip : max gradient norm (train.py:141), 0 disables
     bucket_mb : flat gradient bucket size
     process_group : None -> default group if torch.distributed is initialised
+    accumulation_steps : micro-batches each rank runs per optimizer step (train.py:127-147 on fewer
+        GPUs than micro-batches): ``step`` is then called once per micro-batch, gradients of
+        ``loss / (world * accumulation_steps)`` sum into the buckets, and the all-reduce, clip,
+        optimizer step and EMA update happen on every ``accumulation_steps``-th call
     """
 
     def __init__(self, model, criterion, optimizer, grad_clip: float = 0.0, bucket_mb: float = 24.0,
-                 process_group=None, cuda_graph: bool = False, graph_warmup: int = 3, ema=None):
+                 process_group=None, cuda_graph: bool = False, graph_warmup: int = 3, ema=None,
+                 accumulation_steps: int = 1):
         self.model, self.criterion, self.optimizer, self.grad_clip = model, criterion, optimizer, grad_clip
+        if accumulation_steps < 1:
+            raise ValueError("accumulation_steps must be >= 1")
+        self.accumulation_steps = int(accumulation_steps)
+        self._micro = 0          # micro-batches seen since the last optimizer step
+        self._first = self._last = True   # phase of the micro-batch being run (set by step)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.buckets: List[_Bucket] = []
@@ -117,7 +127,7 @@ class BatchShardedTrainer:
             items, bucket.deferred = bucket.deferred, []
             wgrad_reduce_multi(items, accumulate=True)
             bucket.pending -= len(items)
-        if bucket.pending == 0 and self.world > 1 and bucket.work is None:
+        if bucket.pending == 0 and self.world > 1 and self._last and bucket.work is None:
             bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _defer_reduce(self, param, item) -> None:
@@ -150,11 +160,13 @@ class BatchShardedTrainer:
 
     # ------------------------------------------------------------------ one optimizer step
     def _forward(self, images: torch.Tensor):
-        """First half of a step: zero the gradient buckets, rebuild the weight packs (one launch)
-        and run the model's forward pass.  Does not touch the masks."""
+        """First half of a micro-step: on the first micro-batch of an optimizer step zero the
+        gradient buckets and rebuild the weight packs (one launch); run the model's forward pass.
+        Does not touch the masks."""
         self.model.train()
         for b in self.buckets:
-            b.flat.zero_()
+            if self._first:
+                b.flat.zero_()
             b.pending = len(b.params)
             b.work = None
             b.deferred = []
@@ -164,7 +176,8 @@ class BatchShardedTrainer:
                 from .kernels import WeightPacker
                 self._packer = WeightPacker([m.weight for m in self.model.modules()
                                              if isinstance(m, torch.nn.Conv2d) and m.weight.is_cuda])
-            self._packer.run()
+            if self._first:   # the weights only change at an optimizer step
+                self._packer.run()
         prev_packs, ops.PACKS = ops.PACKS, self._packer
         try:
             return self.model(images)
@@ -172,14 +185,17 @@ class BatchShardedTrainer:
             ops.PACKS = prev_packs
 
     def _backward(self, outputs, masks: torch.Tensor) -> torch.Tensor:
-        """Second half: loss, backward (gradient sink installed), all-reduce, clip + optimizer, EMA."""
+        """Second half: loss, backward (gradient sink installed) and, on the last micro-batch of an
+        optimizer step, all-reduce, clip + optimizer, EMA."""
         prev_sink, ops.GRAD_SINK = ops.GRAD_SINK, _GradSink(self)
         try:
             loss = self.criterion(outputs, masks)
-            (loss / self.world).backward()
+            (loss / (self.world * self.accumulation_steps)).backward()
             self._flush_deferred()
         finally:
             ops.GRAD_SINK = prev_sink
+        if not self._last:
+            return loss.detach()
         if self.world > 1:
             for b in self.buckets:
                 if b.work is None:  # a parameter without gradient this step
@@ -211,9 +227,13 @@ class BatchShardedTrainer:
         (pinned) tensors: they are copied to this rank's GPU asynchronously.  Returns the
         un-divided micro-batch loss as a 0-dim device tensor (no host sync)."""
         dev = next(self.model.parameters()).device
-        self._steps += 1
-        if self.ema is not None:
-            self.ema.prepare(self.model)   # host side: counter, warm-up decay -> device memory
+        self._first = self._micro == 0
+        self._last = self._micro == self.accumulation_steps - 1
+        self._micro = 0 if self._last else self._micro + 1
+        if self._last:
+            self._steps += 1
+            if self.ema is not None:
+                self.ema.prepare(self.model)   # host side: counter, warm-up decay -> device memory
         use_graph = self.cuda_graph and dev.type == "cuda" and self._optimizer_capturable()
         if dev.type != "cuda":
             return self._step_body(images.to(dev), masks.to(dev))
@@ -233,7 +253,8 @@ class BatchShardedTrainer:
             main.wait_event(self._masks_ready)
             masks_dev.record_stream(main)
             return self._backward(outputs, masks_dev)
-        key = (tuple(images.shape), images.dtype, tuple(masks.shape), masks.dtype)
+        # a micro-step's graph depends on its phase (zero + pack first, all-reduce + optimizer last)
+        key = (tuple(images.shape), images.dtype, tuple(masks.shape), masks.dtype, self._first, self._last)
         entry = self._graphs.get(key)
         if entry is None:
             done = self._eager_steps.get(key, 0)
@@ -269,7 +290,7 @@ class BatchShardedTrainer:
         with torch.cuda.stream(copy):
             gt.copy_(masks, non_blocking=True)
             self._masks_ready.record(copy)
-        if isinstance(self.optimizer, FusedAdamW):
+        if self._last and isinstance(self.optimizer, FusedAdamW):
             self.optimizer.sync_hyperparams()   # a scheduler may have changed the learning rate
         g_fwd.replay()
         main.wait_event(self._masks_ready)
