@@ -245,6 +245,10 @@ class BatchShardedTrainer:
             self._masks_ready = torch.cuda.Event()
             self._step_done = torch.cuda.Event()
         copy = self._copy_stream
+        if masks.is_cuda:
+            # device-resident masks (e.g. from unet.data.DeviceBatchPipeline) were produced by work the
+            # caller's stream already waits for: order the copy stream behind it as well
+            copy.wait_stream(main)
         if not use_graph:
             with torch.cuda.stream(copy):
                 masks_dev = masks.to(dev, non_blocking=True)
