@@ -136,6 +136,13 @@ int ub2_upsample_fwd(const void* in, int ld_in, void* out, int ld_out, int N, in
 int ub2_upsample_bwd(const void* dout, int ld_dout, void* din, int ld_din, int accumulate, int N,
                      int hin, int win, int hu, int wu, int Ho, int Wo, int C, void* stream);
 
+/* F.interpolate(x, size, mode='bilinear', align_corners=True) of the deep-supervision logits
+ * (unet/models/unet.py:206-208) and its transpose in gather form (deterministic): fp32 NCHW,
+ * planes = N * channels, (hin,win) -> (Ho,Wo), any scale. */
+int ub2_resize_planes_fwd(const float* in, float* out, int planes, int hin, int win, int Ho, int Wo, void* stream);
+int ub2_resize_planes_bwd(const float* dout, float* din, int planes, int hin, int win, int Ho, int Wo,
+                          void* stream);
+
 /* ======================= attention gate (layers.py:171-192) ============================= */
 /* q = W_g.g at low resolution and xp = W_x.x come from ub2_conv_fwd (taps = 1).           */
 

@@ -46,3 +46,33 @@ def test_upsample_fwd_bwd(n, hin, win, hu, wu, ho, wo, c):
     acc = base.clone().cuda()
     K.upsample_bwd(dout.cuda(), hin, win, hu, wu, into=acc)
     assert torch.allclose(acc.float().cpu(), ref_g + base.float(), rtol=2 ** -6, atol=2 ** -5)
+
+
+@pytest.mark.parametrize("n,c,h,w,ho,wo", [
+    (2, 2, 64, 64, 512, 512),     # ds_out3: x8
+    (2, 2, 128, 128, 512, 512),   # ds_out2: x4
+    (1, 2, 256, 256, 512, 512),   # ds_out1: x2
+    (3, 3, 7, 9, 20, 31),         # odd sizes, any ratio
+    (1, 2, 1, 5, 4, 5),           # a single source row; unchanged width
+    (2, 1, 6, 6, 1, 1),           # to a single pixel (scale 0)
+    (1, 2, 16, 16, 8, 12),        # down-sampling
+])
+def test_resize_logits_fwd_bwd(n, c, h, w, ho, wo):
+    """ops.resize_logits == F.interpolate(bilinear, align_corners=True) on fp32 NCHW, forward and
+    backward (ATen's CUDA kernel as the fp32 reference; gradient in gather form, deterministic)."""
+    from unet import ops
+    g = torch.Generator().manual_seed(h * 100 + wo)
+    x = torch.randn(n, c, h, w, generator=g).cuda()
+    dy = torch.randn(n, c, ho, wo, generator=g).cuda()
+    xr = x.clone().requires_grad_(True)
+    ref = F.interpolate(xr, size=(ho, wo), mode="bilinear", align_corners=True)
+    ref.backward(dy)
+    xo = x.clone().requires_grad_(True)
+    out = ops.resize_logits(xo, (ho, wo))
+    out.backward(dy)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+    scale = max(1.0, (ho / h) * (wo / w))
+    assert torch.allclose(xo.grad, xr.grad, rtol=1e-4, atol=1e-5 * scale)
+    out2 = ops.resize_logits(x, (ho, wo))
+    assert torch.equal(out2, out.detach())

@@ -424,6 +424,61 @@ static UpGeom up_geom(int N, int hin, int win, int hu, int wu, int Ho, int Wo, i
   return g;
 }
 
+// ------------------------------------------------------------------------------ fp32 planes
+// F.interpolate(logits, size, mode='bilinear', align_corners=True) of the deep-supervision heads
+// (unet/models/unet.py:206-208): fp32 NCHW planes (N * n_classes of them), any scale.  Same index
+// arithmetic and summation form as ATen's upsample_bilinear2d.  A few MB per step: one thread
+// per pixel.
+__global__ void __launch_bounds__(256)
+resize_planes_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, LowRes g) {
+  const long long total = static_cast<long long>(planes) * g.Ho * g.Wo;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wo = static_cast<int>(idx % g.Wo);
+    const long long row = idx / g.Wo;
+    const int ho = static_cast<int>(row % g.Ho);
+    const long long p = row / g.Ho;
+    int h0, h1, w0, w1;
+    float a0, a1, b0, b1;
+    src_index(g.rh, ho, g.hin, h0, h1, a0, a1);
+    src_index(g.rw, wo, g.win, w0, w1, b0, b1);
+    const float* base = in + p * g.hin * g.win;
+    const float v00 = __ldg(base + h0 * g.win + w0), v01 = __ldg(base + h0 * g.win + w1);
+    const float v10 = __ldg(base + h1 * g.win + w0), v11 = __ldg(base + h1 * g.win + w1);
+    out[idx] = a0 * (b0 * v00 + b1 * v01) + a1 * (b0 * v10 + b1 * v11);
+  }
+}
+
+// Its transpose in gather form: din[p][i][j] = sum over the destination pixels that read (i,j).
+// Deterministic (ATen scatters with atomics).
+__global__ void __launch_bounds__(256)
+resize_planes_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int planes, LowRes g) {
+  const long long total = static_cast<long long>(planes) * g.hin * g.win;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(idx % g.win);
+    const long long row = idx / g.win;
+    const int i = static_cast<int>(row % g.hin);
+    const long long p = row / g.hin;
+    int ylo, yhi, xlo, xhi;
+    dst_range(g.rh, i, g.Ho, ylo, yhi);
+    dst_range(g.rw, j, g.Wo, xlo, xhi);
+    const float* base = dout + p * g.Ho * g.Wo;
+    float acc = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      const float wy = tap_weight(g.rh, y, g.hin, i);
+      if (wy == 0.f) continue;
+      float rowacc = 0.f;
+      for (int x = xlo; x <= xhi; ++x) {
+        const float wx = tap_weight(g.rw, x, g.win, j);
+        if (wx != 0.f) rowacc = fmaf(wx, __ldg(base + static_cast<long long>(y) * g.Wo + x), rowacc);
+      }
+      acc = fmaf(wy, rowacc, acc);
+    }
+    din[idx] = acc;
+  }
+}
+
 }  // namespace ub2
 
 using namespace ub2;
@@ -478,6 +533,23 @@ int ub2_upsample_bwd(const void* dout, int ld_dout, void* din, int ld_din, int a
   upsample_bwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din,
       accumulate, g);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_resize_planes_fwd(const float* in, float* out, int planes, int hin, int win, int Ho, int Wo, void* stream) {
+  if (planes <= 0 || hin <= 0 || win <= 0 || Ho <= 0 || Wo <= 0) return UB2_ERR_SHAPE;
+  const long long total = static_cast<long long>(planes) * Ho * Wo;
+  resize_planes_fwd_kernel<<<stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, out, planes, make_lowres(hin, win, Ho, Wo));
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_resize_planes_bwd(const float* dout, float* din, int planes, int hin, int win, int Ho, int Wo,
+                          void* stream) {
+  if (planes <= 0 || hin <= 0 || win <= 0 || Ho <= 0 || Wo <= 0) return UB2_ERR_SHAPE;
+  const long long total = static_cast<long long>(planes) * hin * win;
+  resize_planes_bwd_kernel<<<stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dout, din, planes, make_lowres(hin, win, Ho, Wo));
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -520,3 +520,21 @@ def predict_mask(logits, threshold=0.5, mask=None, positives=None):
     _C.call("ub2_predict_mask", ptr(logits), n, c, c_longlong(h * w), c_float(threshold), ptr(mask), ptr(positives),
             stream())
     return mask, positives
+
+
+def resize_planes(x, ho, wo):
+    """fp32 (N,C,h,w) -> (N,C,ho,wo), bilinear, align_corners=True (the deep-supervision resize)."""
+    assert x.dim() == 4 and x.dtype == F32 and x.is_contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, ho, wo), device=x.device, dtype=F32)
+    _C.call("ub2_resize_planes_fwd", ptr(x), ptr(out), n * c, h, w, ho, wo, stream())
+    return out
+
+
+def resize_planes_bwd(dout, h, w):
+    """Transpose of resize_planes: fp32 (N,C,ho,wo) -> (N,C,h,w)."""
+    assert dout.dim() == 4 and dout.dtype == F32 and dout.is_contiguous()
+    n, c, ho, wo = dout.shape
+    din = torch.empty((n, c, h, w), device=dout.device, dtype=F32)
+    _C.call("ub2_resize_planes_bwd", ptr(dout), ptr(din), n * c, h, w, ho, wo, stream())
+    return din

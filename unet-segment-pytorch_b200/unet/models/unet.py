@@ -10,8 +10,8 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
+from .. import ops
 from .layers import AttentionUp, DoubleConv, Down, OutConv, Up
 
 
@@ -100,7 +100,7 @@ class AttentionUNet(_UNetBase):
         logits = self.outc(d1)
         if self.deep_supervision and self.training:
             # auxiliary heads (unet.py:204-209): 2-channel logits, resampled to the input size
-            ds = [F.interpolate(head(d), size=size, mode='bilinear', align_corners=True)
+            ds = [ops.resize_logits(head(d), size)
                   for head, d in ((self.ds_out1, d2), (self.ds_out2, d3), (self.ds_out3, d4))]
             return [logits] + ds
         return logits

@@ -244,6 +244,28 @@ class Upsample2x(torch.autograd.Function):
         return from_nhwc(K.upsample_bwd(to_nhwc(dout), h, w, hu, wu)), None, None
 
 
+class ResizeLogits(torch.autograd.Function):
+    """F.interpolate(logits, size, mode='bilinear', align_corners=True) of the deep-supervision heads
+    (unet/models/unet.py:206-208): fp32 NCHW in and out."""
+
+    @staticmethod
+    def forward(ctx, x, out_h, out_w):
+        x = x.contiguous()
+        ctx.geom = (x.shape[2], x.shape[3])
+        return K.resize_planes(x, out_h, out_w)
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, w = ctx.geom
+        return K.resize_planes_bwd(dout.contiguous(), h, w), None, None
+
+
+def resize_logits(x, size):
+    if not x.is_cuda:
+        raise RuntimeError("unet-b200 ops need CUDA tensors: there is no CPU fallback")
+    return ResizeLogits.apply(x.float(), int(size[0]), int(size[1]))
+
+
 class AttentionGateFn(torch.autograd.Function):
     """AttentionGate.forward (layers.py:171-192) as two tensor-core 1x1 projections plus three
     bandwidth-bound passes; see csrc/gate.cu."""
