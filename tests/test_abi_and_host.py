@@ -119,3 +119,25 @@ def test_input_pipeline_host_side():
         DeviceBatchPipeline([], "cpu")
     with pytest.raises(RuntimeError, match="CUDA"):
         prepare_batch(torch.zeros(1, 16, 16, dtype=torch.uint8))
+
+
+def test_host_side_argument_checks():
+    """Constructor-level behaviour that needs no GPU: bad arguments raise, CPU models are refused
+    by the engines that only exist for the CUDA path."""
+    import torch.nn as nn
+    from unet.inference import InferenceEngine
+    from unet.models import AttentionUNet
+    from unet.parallel import BatchShardedTrainer
+    lin = nn.Linear(2, 2)
+    with pytest.raises(ValueError, match="accumulation_steps"):
+        BatchShardedTrainer(lin, nn.MSELoss(), torch.optim.SGD(lin.parameters(), lr=0.1), accumulation_steps=0)
+    tr = BatchShardedTrainer(lin, nn.MSELoss(), torch.optim.SGD(lin.parameters(), lr=0.1), accumulation_steps=2)
+    assert tr.accumulation_steps == 2 and tr.world == 1 and len(tr.buckets) == 1
+    # gradients live in one flat bucket, every view on a 128-byte boundary
+    assert all(p.grad is not None and p.grad.data_ptr() % 128 == tr.buckets[0].flat.data_ptr() % 128
+               for p in lin.parameters())
+    engine = InferenceEngine(AttentionUNet(1, 2, True, 16))      # building on the CPU is allowed (train.py:306)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        engine(torch.zeros(1, 1, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        engine.predict(torch.zeros(1, 32, 32, dtype=torch.uint8))
