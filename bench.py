@@ -37,6 +37,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "AttentionUNet 512^2 train images/sec (whole job; per GPU = value / n_gpus)"
 H = W = 512
+WORKLOAD = ("AttentionUNet(1,2,bilinear,64) train step: fwd + DiceBCELoss + bwd + clip 1.0 + AdamW, "
+            "1x512x512 inputs (BASELINE configs[1])")
 
 
 def load_peaks():
@@ -153,8 +155,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "AttentionUNet(1,2,bilinear,64) train step 512x512 (BASELINE configs[1] shape)",
-                   "batch_per_step": batch},
+        "config": {"workload": WORKLOAD, "batch_per_step": batch},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -314,8 +315,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "AttentionUNet(1,2,bilinear,64) train step: fwd + DiceBCELoss + bwd + clip 1.0 + AdamW, "
-                               "1x512x512 inputs (BASELINE configs[1])",
+        "config": {"workload": WORKLOAD,
                    "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world} (batch sharded, NCCL all-reduce overlapped with backward)",
                    "cuda_graph": not args.no_graph,
