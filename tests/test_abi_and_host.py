@@ -1,7 +1,6 @@
 """CPU: the C-ABI library loads and exports every symbol include/unetb200.h declares, and the
 host-side mirror of the reference interface behaves (no compute calls: there is no GPU here)."""
 import copy
-import ctypes
 import os
 import re
 

@@ -17,7 +17,7 @@ code runs without collectives.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.distributed as dist
