@@ -157,7 +157,6 @@ seg_stats_bwd_kernel(const float* __restrict__ logits, const long long* __restri
   const long long* t = targets + static_cast<size_t>(n) * HW;
   float* dz = dlogits + static_cast<size_t>(n) * C * HW;
   float dce[C], dI[C], dP[C];
-#pragma unroll
   const float gs = gscale != nullptr ? __ldg(gscale) : 1.f;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
