@@ -1,6 +1,7 @@
 """CPU: the C-ABI library loads and exports every symbol include/unetb200.h declares, and the
 host-side mirror of the reference interface behaves (no compute calls: there is no GPU here)."""
 import copy
+import ctypes
 import os
 import re
 
@@ -140,3 +141,27 @@ def test_host_side_argument_checks():
         engine(torch.zeros(1, 1, 32, 32))
     with pytest.raises(RuntimeError, match="CUDA"):
         engine.predict(torch.zeros(1, 32, 32, dtype=torch.uint8))
+
+
+def test_workspace_queries_and_argument_errors_on_the_host():
+    """The *_rows / *_blocks queries are pure host arithmetic (no device needed): positive counts for
+    valid shapes, UB2_ERR_SHAPE (-1) for degenerate or unsupported ones, and entry points reject NULL /
+    unsupported arguments before touching the device."""
+    from unet import _C
+    lib = _C.lib()
+    lib.ub2_seg_stats_blocks.argtypes = [ctypes.c_int, ctypes.c_longlong]
+    assert lib.ub2_adamw_chunk_elems() == 16384
+    good = (4, 512, 512, 64)
+    queries = [lib.ub2_outc_rows, lib.ub2_conv_in_rows, lib.ub2_gate_rows, lib.ub2_gate_strip_rows,
+               lambda n, h, w, c: lib.ub2_bn_bwd_rows(n, h, w, c, 0), lambda n, h, w, c: lib.ub2_bn_bwd_rows(n, h, w, c, 1)]
+    for q in queries:
+        assert 0 < q(*good) <= 148 * 16
+        for bad in ((0, 512, 512, 64), (4, 0, 512, 64), (4, 512, 0, 64), (-1, 8, 8, 8), (4, 512, 512, 60), (4, 512, 512, 0)):
+            assert q(*bad) == -1, bad
+    assert lib.ub2_seg_stats_blocks(4, 512 * 512) > 0
+    assert lib.ub2_seg_stats_blocks(0, 512 * 512) == -1 and lib.ub2_seg_stats_blocks(2, 0) == -1
+    f = ctypes.c_float
+    assert lib.ub2_prepare_batch(None, None, None, 1, 8, 8, f(0.5), f(0.5), None, None, None) == -1
+    assert lib.ub2_predict_mask(None, 1, 2, ctypes.c_longlong(64), f(0.5), None, None, None) == -1
+    assert lib.ub2_resize_planes_fwd(None, None, 0, 1, 1, 1, 1, None) == -1
+    assert lib.ub2_resize_planes_bwd(None, None, 2, 0, 1, 1, 1, None) == -1

@@ -350,7 +350,8 @@ int ub2_bn_eval_coeffs(const float* gamma, const float* beta, const float* runni
 int ub2_bn_act(const void* y, int ld_y, const float* scale, const float* shift, void* a, int ld_a,
                void* pooled, int ld_p, unsigned char* pidx, int N, int H, int W, int C, int relu,
                void* stream) {
-  if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || !fits32(N, H, W, C)) return UB2_ERR_SHAPE;
+  if (C <= 0 || C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || H <= 0 || W <= 0 || !fits32(N, H, W, C))
+    return UB2_ERR_SHAPE;
   if (ld_y % 8 || (a && ld_a % 8) || (pooled && ld_p % 8)) return UB2_ERR_ALIGN;
   WinGeom g = make_geom(N, H, W, C);
   const int block = bn_block(g.cgs);
@@ -367,7 +368,7 @@ static int bwd_items(const WinGeom& g, bool pool) {
 }
 
 int ub2_bn_bwd_rows(int N, int H, int W, int C, int pool) {
-  if (C % 8 != 0 || C / 8 > kBnThreads) return UB2_ERR_SHAPE;
+  if (C <= 0 || C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || H <= 0 || W <= 0) return UB2_ERR_SHAPE;
   WinGeom g = make_geom(N, H, W, C);
   const int lanes = bn_block(g.cgs) / g.cgs;
   return stream_grid((bwd_items(g, pool != 0) + 3) / 4, lanes, num_sms(), 2);
@@ -376,7 +377,8 @@ int ub2_bn_bwd_rows(int N, int H, int W, int C, int pool) {
 int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, const unsigned char* pidx,
                       const void* y, int ld_y, const float* scale, const float* shift, double* partials,
                       int rows, int N, int H, int W, int C, int relu, void* stream) {
-  if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || !fits32(N, H, W, C)) return UB2_ERR_SHAPE;
+  if (C <= 0 || C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || H <= 0 || W <= 0 || !fits32(N, H, W, C))
+    return UB2_ERR_SHAPE;
   if ((dA == nullptr && dP == nullptr) || (dP != nullptr && pidx == nullptr)) return UB2_ERR_SHAPE;
   WinGeom g = make_geom(N, H, W, C);
   const bool pool = dP != nullptr;
@@ -405,7 +407,8 @@ int ub2_bn_bwd_finalize(const double* partials, int rows, int C, double count, c
 int ub2_bn_bwd_apply(const void* dA, int ld_da, const void* dP, int ld_dp, const unsigned char* pidx,
                      const void* y, int ld_y, const float* scale, const float* shift, const float* coef,
                      void* dY, int ld_dy, int N, int H, int W, int C, int relu, void* stream) {
-  if (C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || !fits32(N, H, W, C)) return UB2_ERR_SHAPE;
+  if (C <= 0 || C % 8 != 0 || C / 8 > kBnThreads || N <= 0 || H <= 0 || W <= 0 || !fits32(N, H, W, C))
+    return UB2_ERR_SHAPE;
   if ((dA == nullptr && dP == nullptr) || (dP != nullptr && pidx == nullptr)) return UB2_ERR_SHAPE;
   WinGeom g = make_geom(N, H, W, C);
   const bool pool = dP != nullptr;

@@ -38,7 +38,7 @@ static int gate_tpp(int cgs) {
   return t;
 }
 static int make_gate_geom(GateGeom* g, int N, int H, int W, int C, int hin, int win) {
-  if (C % 8 != 0 || N <= 0 || H <= 0 || W <= 0) return UB2_ERR_SHAPE;
+  if (C <= 0 || C % 8 != 0 || N <= 0 || H <= 0 || W <= 0) return UB2_ERR_SHAPE;
   if (static_cast<double>(N) * H * W * (C / 8) >= 2.0e9) return UB2_ERR_SHAPE;  // 32-bit pixel indices
   g->N = N; g->H = H; g->W = W; g->C = C; g->cgs = C / 8;
   g->tpp = gate_tpp(g->cgs);

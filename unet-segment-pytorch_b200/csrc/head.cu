@@ -528,7 +528,7 @@ __global__ void outc_bwd_finalize_kernel(const double* __restrict__ partials, in
 }
 
 static int head_geom(HeadGeom* g, int N, int H, int W, int C, int K) {
-  if (C % 8 != 0 || K < 1 || K > kMaxClasses || N <= 0) return UB2_ERR_SHAPE;
+  if (C <= 0 || C % 8 != 0 || K < 1 || K > kMaxClasses || N <= 0 || H <= 0 || W <= 0) return UB2_ERR_SHAPE;
   if (static_cast<double>(N) * H * W * K >= 2.0e9) return UB2_ERR_SHAPE;  // 32-bit pixel indices
   g->C = C; g->cgs = C / 8; g->K = K;
   int t = 1;
@@ -547,7 +547,7 @@ using namespace ub2;
 extern "C" {
 
 int ub2_conv_in_rows(int N, int H, int W, int Cout) {
-  if (Cout % 8 != 0 || Cout / 8 > kHeadThreads) return UB2_ERR_SHAPE;
+  if (Cout <= 0 || Cout % 8 != 0 || Cout / 8 > kHeadThreads || N <= 0 || H <= 0 || W <= 0) return UB2_ERR_SHAPE;
   const int lanes = kHeadThreads / (Cout / 8);
   return stream_grid(static_cast<int>(N) * H * W, lanes, num_sms(), 4);
 }

@@ -213,7 +213,10 @@ using namespace ub2;
 
 extern "C" {
 
-int ub2_seg_stats_blocks(int N, long long HW) { return loss_blocks(N, HW); }
+int ub2_seg_stats_blocks(int N, long long HW) {
+  if (N <= 0 || HW <= 0) return UB2_ERR_SHAPE;
+  return loss_blocks(N, HW);
+}
 
 int ub2_seg_stats(const float* logits, const long long* targets, int N, int C, long long HW,
                   double* partials, int blocks, float* stats, void* stream) {

@@ -282,7 +282,7 @@ int ub2_pack_conv_weight(const float* w, void* fwd, void* dgrad, int Cout, int C
 }
 
 int ub2_wgrad_reduce_multi(const Ub2ReduceItem* items, int n, int accumulate, void* stream) {
-  if (n <= 0 || n > UB2_REDUCE_MAX_ITEMS) return UB2_ERR_SHAPE;
+  if (items == nullptr || n <= 0 || n > UB2_REDUCE_MAX_ITEMS) return UB2_ERR_SHAPE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ReduceItems pre{}, red{};
   int pre_blocks = 0, red_blocks = 0;

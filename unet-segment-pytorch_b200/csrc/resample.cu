@@ -487,7 +487,8 @@ extern "C" {
 
 int ub2_upsample_fwd(const void* in, int ld_in, void* out, int ld_out, int N, int hin, int win, int hu,
                      int wu, int Ho, int Wo, int C, void* stream) {
-  if (C % 8 != 0 || Ho < hu || Wo < wu || N <= 0) return UB2_ERR_SHAPE;
+  if (C <= 0 || C % 8 != 0 || Ho < hu || Wo < wu || N <= 0 || hin <= 0 || win <= 0 || hu <= 0 || wu <= 0)
+    return UB2_ERR_SHAPE;
   if (ld_in % 8 || ld_out % 8) return UB2_ERR_ALIGN;
   UpGeom g = up_geom(N, hin, win, hu, wu, Ho, Wo, C);
   if (Ho >= 2 * kStripRows) {
@@ -506,7 +507,8 @@ int ub2_upsample_fwd(const void* in, int ld_in, void* out, int ld_out, int N, in
 
 int ub2_upsample_bwd(const void* dout, int ld_dout, void* din, int ld_din, int accumulate, int N,
                      int hin, int win, int hu, int wu, int Ho, int Wo, int C, void* stream) {
-  if (C % 8 != 0 || Ho < hu || Wo < wu || N <= 0) return UB2_ERR_SHAPE;
+  if (C <= 0 || C % 8 != 0 || Ho < hu || Wo < wu || N <= 0 || hin <= 0 || win <= 0 || hu <= 0 || wu <= 0)
+    return UB2_ERR_SHAPE;
   if (ld_dout % 8 || ld_din % 8) return UB2_ERR_ALIGN;
   UpGeom g = up_geom(N, hin, win, hu, wu, Ho, Wo, C);
   if (bwd_strip_ok(g)) {
