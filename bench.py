@@ -293,8 +293,8 @@ def run_ours(args):
                         f"same launches: {tj['algorithmic_bytes_per_launch']:.3e}")
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "conv_fwd_kernel / conv_halo_kernel (3x3 and 1x1 forward + "
-                                             "data-gradient implicit GEMM, tcgen05)",
+    roofline = {"bound": "tensor", "kernel": "conv_halo2_kernel / conv_fwd2_kernel / conv_fwd_kernel (3x3 and 1x1 forward + "
+                                             "data-gradient implicit GEMM, tcgen05, one- and two-CTA)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_note": traffic_note, "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a step)",
                 "launches_per_step": len(prof) // prof_steps, "kernel_ms_per_step": conv_ms_per_step,
