@@ -165,3 +165,34 @@ def test_workspace_queries_and_argument_errors_on_the_host():
     assert lib.ub2_predict_mask(None, 1, 2, ctypes.c_longlong(64), f(0.5), None, None, None) == -1
     assert lib.ub2_resize_planes_fwd(None, None, 0, 1, 1, 1, 1, None) == -1
     assert lib.ub2_resize_planes_bwd(None, None, 2, 0, 1, 1, 1, None) == -1
+
+
+def test_convolution_kernels_are_tcgen05_tma_code():
+    """The built library's convolution kernels contain the SASS that tcgen05.mma / tcgen05.ld / TMA compile
+    to on sm_100a (UTCHMMA, LDTM, UTMALDG: /opt/skills/guides/B200_PROFILING.md), and no legacy HMMA:
+    the tensor-core path is the Blackwell one, not a recompiled mma.sync kernel."""
+    import shutil
+    import subprocess
+    from unet import _C
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", _C.LIB_PATH], capture_output=True, text=True).stdout
+    per_kernel, name = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per_kernel[name] = set()
+            continue
+        if name:
+            for op in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR"):
+                if op in line:
+                    per_kernel[name].add(op)
+            if re.search(r"(?<![A-Z])HMMA", line):     # mma.sync / wmma
+                per_kernel[name].add("legacy HMMA")
+    conv = {k: v for k, v in per_kernel.items() if re.search(r"conv_(fwd|fwd2|halo|halo2|wgrad|wgrad2|wgrad_halo|wgrad_halo2)_kernel", k)}
+    assert len(conv) >= 12
+    for k, ops in conv.items():
+        assert {"UTCHMMA", "LDTM", "UTMALDG", "UTCBAR"} <= ops, (k, ops)
+    assert not any("legacy HMMA" in ops for ops in per_kernel.values())
