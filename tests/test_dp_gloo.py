@@ -116,3 +116,71 @@ def test_single_process_accumulation():
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
     for (k, a), (_, b) in zip(model.state_dict().items(), ref.state_dict().items()):
         assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-6), k   # incl. running stats
+
+
+def _diverged_worker(rank, world, port, out):
+    """Ranks that seeded their models differently: the trainer makes rank 0's state everybody's."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unet.parallel import BatchShardedTrainer
+    torch.manual_seed(100 + rank)
+    model = nn.Sequential(nn.Conv2d(1, 4, 3, padding=1), nn.BatchNorm2d(4), nn.ReLU(), nn.Conv2d(4, 2, 1))
+    with torch.no_grad():
+        model[1].running_mean.fill_(float(rank))
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    tr = BatchShardedTrainer(model, nn.CrossEntropyLoss(), opt, grad_clip=1.0)
+    start = [p.detach().clone() for p in model.parameters()] + [model[1].running_mean.clone()]
+    for _ in range(2):
+        tr.step(*_data(rank))
+    drift = model[1].running_mean.clone()       # each rank saw its own shard
+    tr.sync_buffers()                           # policy "rank0"
+    torch.save({"start": start, "params": [p.detach().clone() for p in model.parameters()], "drift": drift,
+                "synced": model[1].running_mean.clone()}, f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_ranks_start_from_rank0_and_buffers_follow_the_policy(tmp_path):
+    out = str(tmp_path / "r")
+    mp.spawn(_diverged_worker, args=(2, 29615, out), nprocs=2, join=True)
+    r0, r1 = (torch.load(f"{out}.{r}", weights_only=False) for r in range(2))
+    for a, b in zip(r0["start"], r1["start"]):
+        assert torch.equal(a, b)                # broadcast at construction (parameters AND buffers)
+    for a, b in zip(r0["params"], r1["params"]):
+        assert torch.equal(a, b)                # identical updates afterwards
+    assert not torch.equal(r0["drift"], r1["drift"])
+    assert torch.equal(r0["synced"], r1["synced"]) and torch.equal(r0["synced"], r0["drift"])
+
+
+def test_flush_applies_the_left_over_micro_batches():
+    """An epoch of 4 micro-batches with accumulation_steps 3 (train.py:153-159): one full step, then the
+    tail step on the single left-over micro-batch, un-rescaled."""
+    from unet.parallel import BatchShardedTrainer
+    model = _model()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    tr = BatchShardedTrainer(model, nn.CrossEntropyLoss(), opt, grad_clip=1.0, accumulation_steps=3)
+    for m in range(4):
+        tr.step(*_data(m))
+    assert tr.flush() is True and tr.flush() is False
+    tr.step(*_data(0))      # the next epoch starts a fresh window: gradients are zeroed first
+
+    ref = _model()
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    crit = nn.CrossEntropyLoss()
+    ref.train()
+    ropt.zero_grad()
+    for i in range(4):
+        x, t = _data(i)
+        (crit(ref(x), t) / 3).backward()
+        if (i + 1) % 3 == 0:
+            torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+            ropt.step()
+            ropt.zero_grad()
+    torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+    ropt.step()
+    ropt.zero_grad()
+    for a, b in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    x, t = _data(0)
+    (crit(ref(x), t) / 3).backward()
+    for a, b in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-7)

@@ -19,8 +19,17 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of another CTA of the cluster.  No cluster-scope release: that form compiles to
+// MEMBAR.ALL.GPU + ERRBAR in front of the arrive (every epilogue warp then waits for its own output stores
+// before handing the accumulator back; 14-25 % of the stall samples of the 512^2 launches,
+// profiles/r01_ncu_conv_b4_source.md).  The accumulator hand-over needs only TMEM ordering, which
+// tcgen05.fence::before_thread_sync provides.  UB2_RELEASE_ARRIVE restores the old form (A/B builds).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#ifdef UB2_RELEASE_ARRIVE
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 // TMA loads whose completion is signalled on a barrier of the cluster (the leader's)
 __device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,

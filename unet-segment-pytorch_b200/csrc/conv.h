@@ -86,6 +86,17 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C,
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
                  uint32_t bc, uint32_t br, int swizzle_bytes, int elem_bytes = 2);
 int num_sms();
+// Launch state that is per device (function attributes and occupancy belong to a context, and two B200s
+// of one box need not have the same number of complete TPCs): every `static` cache of the launchers is
+// one slot per device ordinal.  Slots hold idempotent results, so a racing first use by two host
+// threads (forward thread / autograd thread) writes the same value twice.
+constexpr int kMaxDevices = 64;
+int device_index();   // current CUDA device, clamped to [0, kMaxDevices)
+template <typename T>
+struct PerDevice {
+  T v[kMaxDevices] = {};
+  T& ref() { return v[device_index()]; }
+};
 
 inline int conv_wide_store_ok(const void* out0, int ld0, const void* out1, int ld1, int split, int Cout) {
   if ((reinterpret_cast<uintptr_t>(out0) & 31) != 0 || ld0 % 16 != 0 || Cout % 16 != 0) return 0;

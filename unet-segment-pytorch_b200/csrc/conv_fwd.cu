@@ -322,7 +322,8 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   if (a.stats && grid > a.stats_rows) return UB2_ERR_WORKSPACE;
   const size_t smem = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(FwdSmemHeader) +
                       stats_bytes;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.ref();
   if (!attr_set) {
     cudaError_t e = cudaSuccess;
     const int lim = 227 * 1024;

@@ -235,7 +235,9 @@ int conv_fwd2_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   if (m_tiles < 2) return 1;
   const int split = (a.out1 != nullptr) ? a.split : (1 << 30);
 
-  static int max_clusters[4] = {0, 0, 0, 0};
+  struct Mc4 { int v[4]; int& operator[](int i) { return v[i]; } };
+  static PerDevice<Mc4> max_clusters_pd;
+  Mc4& max_clusters = max_clusters_pd.ref();
   int BN = a.Cout <= 256 ? a.Cout : 256;
   // few pixel tiles: halve the N tile so that the cluster grid covers the chip
   const int sms = num_sms();

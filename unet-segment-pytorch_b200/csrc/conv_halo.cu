@@ -308,7 +308,8 @@ int conv_halo_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   if (a.stats && grid > a.stats_rows) return UB2_ERR_WORKSPACE;
   const size_t smem = 1024 + 2 * static_cast<size_t>(p.a_bytes) + static_cast<size_t>(b_stages) * p.b_stage_bytes +
                       sizeof(HaloSmemHeader) + stats_bytes;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.ref();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);

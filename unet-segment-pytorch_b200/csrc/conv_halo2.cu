@@ -310,7 +310,8 @@ int conv_halo2_launch(const ConvFwdArgs& a, cudaStream_t stream) {
 
   const size_t smem = 1024 + 2 * static_cast<size_t>(p.a_bytes) + static_cast<size_t>(b_stages) * p.b_stage_bytes +
                       sizeof(Halo2SmemHeader) + stats_bytes;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.ref();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
@@ -323,7 +324,9 @@ int conv_halo2_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   const bool acc = a.stats != nullptr && bn_cols <= 64;
   // Persistent grid = the number of CTA pairs that can be resident at once: a pair needs both SMs
   // of one TPC, and not every TPC of the chip has two (floor-sweeping), so this is < SMs / 2.
-  static int max_clusters[2] = {0, 0};
+  struct Mc2 { int v[2]; int& operator[](int i) { return v[i]; } };
+  static PerDevice<Mc2> max_clusters_pd;
+  Mc2& max_clusters = max_clusters_pd.ref();
   if (max_clusters[acc] == 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * (num_sms() / 2));

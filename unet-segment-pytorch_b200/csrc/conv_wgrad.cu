@@ -307,7 +307,8 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   const int total_items = tiles * splits;
   int grid = sms < total_items ? sms : total_items;
   const size_t smem = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(WgSmemHeader);
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.ref();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -280,7 +280,8 @@ int conv_wgrad2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   if (stages > kW2MaxStages) stages = kW2MaxStages;
   p.stages = stages;
 
-  static int max_clusters = 0;
+  static PerDevice<int> max_clusters_pd;
+  int& max_clusters = max_clusters_pd.ref();
   if (max_clusters == 0) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaLaunchConfig_t cfg = {};

@@ -296,7 +296,8 @@ int conv_wgrad_halo_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   const int grid = items < num_sms() ? items : num_sms();
   const size_t smem = 1024 + 2 * static_cast<size_t>(p.a_bytes) + static_cast<size_t>(b_stages) * p.b_stage_bytes +
                       sizeof(WgHaloHeader);
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_pd;
+  bool& attr_set = attr_set_pd.ref();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);

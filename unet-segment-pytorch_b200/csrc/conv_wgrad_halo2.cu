@@ -307,7 +307,8 @@ int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   p.blocks_h = (a.H + R - 1) / R;
   p.blocks = a.N * p.blocks_h * p.segs_w;
   // resident CTA pairs (see conv_halo2.cu)
-  static int max_clusters = 0;
+  static PerDevice<int> max_clusters_pd;
+  int& max_clusters = max_clusters_pd.ref();
   if (max_clusters == 0) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);

@@ -67,8 +67,18 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows,
   return r == CUDA_SUCCESS ? 0 : UB2_ERR_DRIVER;
 }
 
+int device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
 int num_sms() {
-  static int cached = 0;
+  static PerDevice<int> cache;
+  int& cached = cache.ref();
   if (cached == 0) {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) == cudaSuccess &&

@@ -13,7 +13,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_PKG, "lib", "libunetb200.so")
+# UB2_LIB: another build of the same library (same-box A/B runs of a kernel change, tools/ab_lib.sh)
+LIB_PATH = os.environ.get("UB2_LIB") or os.path.join(_PKG, "lib", "libunetb200.so")
 
 _lib = None
 _lock = threading.Lock()
@@ -55,17 +56,33 @@ def check(rc: int, what: str) -> None:
     raise RuntimeError(f"{what}: CUDA error {rc}")
 
 
+# Device of the tensors of the call being assembled (per host thread: forward runs on the main thread,
+# backward on autograd's).  Every wrapper builds its argument list with ptr(...) first and stream() last,
+# so stream() hands out the current stream OF THAT DEVICE and call() launches with that device current —
+# a model on cuda:1 works while cuda:0 is the process's current device (the reference's
+# get_device('cuda:1') pattern).  Tensors of two devices in one call raise.
+_tls = threading.local()
+
+
 def ptr(t):
     """Device pointer of a CUDA tensor (None -> NULL)."""
     if t is None:
         return ctypes.c_void_p(0)
     if not t.is_cuda:
         raise RuntimeError("unet-b200 ops need CUDA tensors: there is no CPU fallback")
+    idx = t.device.index
+    prev = getattr(_tls, "device", None)
+    if prev is None:
+        _tls.device = idx
+    elif prev != idx:
+        _tls.device = None
+        raise RuntimeError(f"unet-b200 op received tensors on cuda:{prev} and cuda:{idx}")
     return ctypes.c_void_p(t.data_ptr())
 
 
 def stream() -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    idx = getattr(_tls, "device", None)
+    return ctypes.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
 
 
 # kernels launched per entry point (default 1); used for the bench's `gpu_launches` claim
@@ -73,11 +90,31 @@ _KERNELS_PER_CALL = {"ub2_conv_in_wgrad": 2, "ub2_outc_bwd": 2, "ub2_seg_stats":
 LAUNCHES = 0
 
 
-def call(name: str, *args) -> None:
+# When set to a list, call() appends (entry point, start event, end event, work) per launch; ``work`` is
+# the wrapper's (algorithmic FLOPs, algorithmic bytes) claim for the call or None.  bench.py's per-kernel
+# roofline table is built from it (eager pass only: a replayed graph has no host hooks).
+PROFILE = None
+
+
+def call(name: str, *args, work=None) -> None:
     global LAUNCHES
     fn = getattr(lib(), name)
     fn.restype = ctypes.c_int
-    check(fn(*args), name)
+    idx = getattr(_tls, "device", None)
+    _tls.device = None
+    prof = PROFILE
+    if idx is not None and idx != torch.cuda.current_device():
+        with torch.cuda.device(idx):
+            rc = fn(*args)
+    elif prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(idx))
+        rc = fn(*args)
+        e1.record(torch.cuda.current_stream(idx))
+        prof.append((name, e0, e1, work))
+    else:
+        rc = fn(*args)
+    check(rc, name)
     LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
 
 

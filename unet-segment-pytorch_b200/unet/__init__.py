@@ -12,3 +12,12 @@ from .models.unet import AttentionUNet, UNet
 
 __all__ = ["UNet", "AttentionUNet", "DoubleConv", "Down", "Up", "OutConv", "AttentionGate", "AttentionUp",
            "set_precision"]
+
+# Everything else of the reference's package (unet.data.dataset, unet.utils.callbacks, unet.utils.plots, …)
+# falls through to an attached reference checkout: see unet/overlay.py.
+import sys as _sys
+
+from . import overlay as _overlay
+
+_overlay.install(_sys.modules[__name__])
+__getattr__ = _overlay.package_getattr(__name__, ())

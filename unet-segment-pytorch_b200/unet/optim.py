@@ -36,6 +36,18 @@ class FusedAdamW(torch.optim.AdamW):
         super().load_state_dict(state_dict)
         self._fz = None   # re-flatten the loaded moments on the next step
 
+    def zero_grad(self, set_to_none: bool = False):
+        """Zero the gradients IN PLACE by default (torch's default drops them): the flat state and the
+        device pointer tables are keyed on the gradient buffers, and a loop in the reference's style
+        (``optimizer.zero_grad()`` after every step, train.py:143) would otherwise re-allocate every
+        gradient and make each step rebuild them.  ``set_to_none=True`` still works, at that price."""
+        if set_to_none:
+            return super().zero_grad(set_to_none=True)
+        for g in self.param_groups:
+            grads = [p.grad for p in g["params"] if p.grad is not None]
+            if grads:
+                torch._foreach_zero_(grads)
+
     def add_param_group(self, param_group):
         super().add_param_group(param_group)
         self._fz = None
@@ -83,7 +95,7 @@ class FusedAdamW(torch.optim.AdamW):
         flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
         flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
         step = torch.zeros(1, device=dev, dtype=torch.float32)
-        loaded_step = None
+        loaded_steps = []
         off = 0
         ptrs = [[], [], [], []]
         for p in params:
@@ -94,14 +106,26 @@ class FusedAdamW(torch.optim.AdamW):
             if "exp_avg" in st:           # state loaded from a checkpoint (or built by torch's AdamW)
                 m.copy_(st["exp_avg"])
                 v.copy_(st["exp_avg_sq"])
-                s = st.get("step", 0)
-                loaded_step = float(s.item()) if isinstance(s, torch.Tensor) else float(s)
+                loaded_steps.append(st.get("step", 0))
             st["exp_avg"], st["exp_avg_sq"], st["step"] = m, v, step[0]
             ptrs[0].append(p.data_ptr()); ptrs[1].append(p.grad.data_ptr())
             ptrs[2].append(m.data_ptr()); ptrs[3].append(v.data_ptr())
             off += pad(n)
-        if loaded_step is not None:
-            step.fill_(loaded_step)
+        if loaded_steps:
+            # one shared step counter: read the loaded values with ONE host sync and refuse a state whose
+            # parameters disagree (a param group added later, a hand-edited checkpoint) instead of
+            # silently letting the last one win
+            dev_steps = [s.detach().float().reshape(()) for s in loaded_steps if isinstance(s, torch.Tensor) and s.is_cuda]
+            vals = [float(s) for s in loaded_steps if not (isinstance(s, torch.Tensor) and s.is_cuda)]
+            if dev_steps:
+                vals += torch.stack(dev_steps).cpu().tolist()
+            if len(loaded_steps) != len(params) and max(vals) > 0:
+                raise RuntimeError("FusedAdamW keeps one step counter for all parameters: the loaded state has "
+                                   "moments for only some of them")
+            if max(vals) != min(vals):
+                raise RuntimeError(f"FusedAdamW keeps one step counter for all parameters: the loaded state has "
+                                   f"steps from {min(vals):g} to {max(vals):g}")
+            step.fill_(vals[0])
         ce = int(_C.lib().ub2_adamw_chunk_elems())
         chunks = [(t, s) for t, p in enumerate(params) for s in range(0, p.numel(), ce)]
         i64 = lambda x: torch.tensor(x, dtype=torch.int64).to(dev)

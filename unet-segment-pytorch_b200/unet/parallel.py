@@ -60,11 +60,20 @@ class BatchShardedTrainer:
         GPUs than micro-batches): ``step`` is then called once per micro-batch, gradients of
         ``loss / (world * accumulation_steps)`` sum into the buckets, and the all-reduce, clip,
         optimizer step and EMA update happen on every ``accumulation_steps``-th call
+    buffer_sync : what happens to the BatchNorm running buffers of the ranks (each rank only sees its own
+        shard, so they drift apart exactly like the reference's buffers move from micro-batch to
+        micro-batch): ``"rank0"`` — rank 0's buffers are THE buffers, broadcast to every rank before
+        ``evaluate`` / by ``sync_buffers()`` (call it before writing a checkpoint on another rank);
+        ``"average"`` — all-reduce mean of running_mean / running_var instead; ``"none"`` — leave them.
+        Training arithmetic never reads the buffers, so the choice does not change any gradient.
+
+    The loss ``step`` returns is a fresh 0-dim device tensor on every call (under graph replay a copy of
+    the graph's static output), so a loop may keep the returned losses and read them later.
     """
 
     def __init__(self, model, criterion, optimizer, grad_clip: float = 0.0, bucket_mb: float = 24.0,
                  process_group=None, cuda_graph: bool = False, graph_warmup: int = 3, ema=None,
-                 accumulation_steps: int = 1):
+                 accumulation_steps: int = 1, buffer_sync: str = "rank0"):
         self.model, self.criterion, self.optimizer, self.grad_clip = model, criterion, optimizer, grad_clip
         if accumulation_steps < 1:
             raise ValueError("accumulation_steps must be >= 1")
@@ -73,6 +82,13 @@ class BatchShardedTrainer:
         self._first = self._last = True   # phase of the micro-batch being run (set by step)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.buffer_sync = buffer_sync
+        self._buffers_dirty = False
+        if self.world > 1:
+            # One model, replicated: every rank starts from rank 0's parameters and buffers (what DDP does at
+            # construction) — ranks that seeded or loaded differently would otherwise average gradients of
+            # different weights without any error.
+            self._broadcast_state()
         self.buckets: List[_Bucket] = []
         self._bucket_of = {}
         self._build_buckets(bucket_mb)
@@ -91,6 +107,28 @@ class BatchShardedTrainer:
         self._eager_steps = {}
         self._copy_stream = None   # mask copies (see step)
         self._masks_ready = self._step_done = None
+
+    # ------------------------------------------------------------------ replicated state
+    def _broadcast_state(self) -> None:
+        with torch.no_grad():
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                               group=self.group)
+
+    @torch.no_grad()
+    def sync_buffers(self, mode: str = None) -> None:
+        """Make the BatchNorm buffers of all ranks equal (see ``buffer_sync``)."""
+        mode = mode or self.buffer_sync
+        self._buffers_dirty = False
+        if self.world == 1 or mode == "none":
+            return
+        src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        for b in self.model.buffers():
+            if mode == "average" and b.is_floating_point():
+                dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group)
+                b.div_(self.world)
+            else:   # rank0; integer counters (num_batches_tracked) are equal on all ranks anyway
+                dist.broadcast(b, src=src, group=self.group)
 
     # ------------------------------------------------------------------ flat gradient buckets
     def _build_buckets(self, bucket_mb: float) -> None:
@@ -196,6 +234,12 @@ class BatchShardedTrainer:
             ops.GRAD_SINK = prev_sink
         if not self._last:
             return loss.detach()
+        self._optimizer_tail()
+        return loss.detach()
+
+    def _optimizer_tail(self) -> None:
+        """All-reduce what is not in flight yet, wait, clip + optimizer step, EMA (train.py:139-147)."""
+        self._buffers_dirty = True
         if self.world > 1:
             for b in self.buckets:
                 if b.work is None:  # a parameter without gradient this step
@@ -212,7 +256,23 @@ class BatchShardedTrainer:
             self.optimizer.step()
         if self.ema is not None:
             self.ema.update(self.model, _advance=False)
-        return loss.detach()
+
+    def flush(self) -> bool:
+        """End of an epoch whose number of micro-batches is not a multiple of ``accumulation_steps``
+        (train.py:153-159): apply the optimizer step to the gradients accumulated so far.  Like the
+        reference, the left-over gradients are NOT rescaled (each micro-batch already carried
+        ``1 / accumulation_steps``).  Returns False if nothing was pending.  Runs eagerly (it happens
+        once per epoch); the next ``step`` starts a fresh accumulation window."""
+        if self._micro == 0:
+            return False
+        self._micro = 0
+        self._steps += 1
+        if self.ema is not None:
+            self.ema.prepare(self.model)
+        for b in self.buckets:
+            b.work = None
+        self._optimizer_tail()
+        return True
 
     def _step_body(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         return self._backward(self._forward(images), masks)
@@ -300,7 +360,7 @@ class BatchShardedTrainer:
         main.wait_event(self._masks_ready)
         g_bwd.replay()
         self._step_done.record(main)
-        return gloss
+        return gloss.clone()   # the graph's static output is overwritten by the next replay
 
     def release_graphs(self) -> None:
         """Drop the captured step graphs (they hold references to NCCL work and pool memory)."""
@@ -312,6 +372,8 @@ class BatchShardedTrainer:
         """validate() of the reference (train.py:164-197) for one batch: eval-mode forward
         (BatchNorm folded, ReLU fused), loss, and device-side confusion-matrix update."""
         dev = next(self.model.parameters()).device
+        if self._buffers_dirty:
+            self.sync_buffers()   # every rank validates the same model (buffer_sync policy)
         images = images.to(dev, non_blocking=True)
         masks = masks.to(dev, non_blocking=True)
         self.model.eval()

@@ -97,3 +97,10 @@ class ModelEMA:
         self.ema_model.load_state_dict(state_dict['ema_state_dict'])
         self.decay = state_dict.get('decay', self.decay)
         self.updates = state_dict.get('updates', 0)
+
+
+# set_seed, get_device, load_config, increment_path (general.py:18-108 of the reference) are host-side
+# orchestration: they resolve to the attached reference checkout's own general.py (unet/overlay.py)
+from .. import overlay as _overlay  # noqa: E402
+
+__getattr__ = _overlay.module_getattr(__name__, "utils/general.py")
