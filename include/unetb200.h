@@ -38,6 +38,10 @@ int ub2_version(void);
 int ub2_num_sms(void);
 /* Tuning / A-B testing: 0 = automatic kernel choice, 1 = never use the halo-resident 3x3 kernel. */
 int ub2_set_conv_mode(int mode);
+/* Which kernel the dispatcher launched for the calling thread's last ub2_conv_fwd / ub2_conv_wgrad call:
+ * forward and data gradient 1 = one CTA per tap, 2 = CTA pair per tap, 3 = one CTA halo-resident,
+ * 4 = CTA pair halo-resident; weight gradient 11..14 in the same order.  Diagnostics / tests only. */
+int ub2_last_conv_variant(void);
 
 /* ======================= convolutions on tcgen05 tensor cores =========================== */
 

@@ -14,6 +14,7 @@ import pytest
 import torch
 
 from oracle import unet_oracle as O
+from parity_log import record
 
 pytestmark = pytest.mark.gpu
 
@@ -65,7 +66,11 @@ def run_oracle(fn, sd, inputs, grad_out, training):
     return out.detach(), [x.grad for x in ins], {k: p.grad for k, p in params.items()}, sd
 
 
-def check_module(module, oracle_fn, inputs, training, seed=0, input_needs_grad=True, out_tol=2e-2):
+def check_module(module, oracle_fn, inputs, training, seed=0, input_needs_grad=True, out_tol=2e-2, tag=None):
+    """``tag``: name under which every measured number goes to the parity log (default: the test's)."""
+    import os
+    tag = tag or os.environ.get("PYTEST_CURRENT_TEST", "module").split("::")[-1].split(" ")[0]
+    log = {}
     torch.manual_seed(seed)
     module = randomise(module, seed + 1)
     module.train(training)
@@ -92,6 +97,8 @@ def check_module(module, oracle_fn, inputs, training, seed=0, input_needs_grad=T
         st_out, st_in, st_par, _ = run_oracle(oracle_fn, sd, inputs, grad_out, training)
     problems = []
     report = [f"out rel-L2: fp32 {rel_l2(out, ref_out):.3e}  bf16-model {rel_l2(out, st_out):.3e}"]
+    log.update(out_rel_l2_vs_fp32=rel_l2(out, ref_out), out_rel_l2_vs_bf16_model=rel_l2(out, st_out),
+               out_rel_l2_floor_bf16_model_vs_fp32=rel_l2(st_out, ref_out))
     if rel_l2(out, ref_out) > out_tol:
         problems.append(f"output rel-L2 vs fp32 {rel_l2(out, ref_out):.3e}")
     if rel_l2(out, st_out) > 5e-3:
@@ -100,6 +107,7 @@ def check_module(module, oracle_fn, inputs, training, seed=0, input_needs_grad=T
         for i, (ci, ri, si) in enumerate(zip(cins, ref_in, st_in)):
             c, e = cosine(ci.grad, ri), rel_l2(ci.grad, si)
             report.append(f"in{i}: cos(fp32) {c:.5f} rel-L2(bf16-model) {e:.3e}")
+            log[f"in{i}_grad"] = {"cos_vs_fp32": c, "rel_l2_vs_bf16_model": e, "cos_floor_bf16_model_vs_fp32": cosine(si, ri)}
             if c < 0.995:
                 problems.append(f"input {i} grad cosine vs fp32 oracle {c:.5f}")
             if e > 2e-2:
@@ -111,6 +119,8 @@ def check_module(module, oracle_fn, inputs, training, seed=0, input_needs_grad=T
         c, c2 = cosine(p.grad, r), cosine(p.grad, r2)
         scale = (p.grad.float().cpu().norm() / r2.norm()).item()
         report.append(f"{name}: cos fp32 {c:.5f} bf16-model {c2:.5f} norm ratio {scale:.4f}")
+        log[f"grad {name}"] = {"cos_vs_fp32": c, "cos_vs_bf16_model": c2, "cos_floor_bf16_model_vs_fp32": cosine(r2, r),
+                               "norm_ratio": scale}
         if c < 0.995:
             problems.append(f"{name}: grad cosine vs fp32 {c:.5f}")
         if c2 < 0.999:
@@ -125,6 +135,7 @@ def check_module(module, oracle_fn, inputs, training, seed=0, input_needs_grad=T
             if k.endswith("num_batches_tracked") and int(v) != int(ref_sd["m." + k]):
                 problems.append(f"{k}: {int(v)} vs {int(ref_sd['m.' + k])}")
     print("\n".join(report))
+    record(tag, shapes=[list(x.shape) for x in inputs], training=training, problems=problems, **log)
     assert not problems, "; ".join(problems)
 
 
@@ -222,9 +233,11 @@ def test_eval_end_to_end(attention, bf):
     ocfg = {k: v for k, v in cfg.items() if k in ("bilinear", "deep_supervision")}
     ref = O.unet_forward(x, sd, attention=attention, training=False, **ocfg)
     assert logits.dtype == torch.float32 and logits.shape == ref.shape
-    assert rel_l2(logits, ref) <= 2e-2, f"eval logits rel-L2 {rel_l2(logits, ref):.3e}"
     m_got = torch.softmax(logits.cpu(), 1)[:, 1] > 0.5
     m_ref = torch.softmax(ref, 1)[:, 1] > 0.5
+    record(f"test_eval_end_to_end[{attention}-{bf}]", logits_rel_l2_vs_fp32=rel_l2(logits, ref),
+           mask_agreement=(m_got == m_ref).float().mean().item(), shape=list(x.shape))
+    assert rel_l2(logits, ref) <= 2e-2, f"eval logits rel-L2 {rel_l2(logits, ref):.3e}"
     assert (m_got == m_ref).float().mean().item() >= 0.999
 
 
@@ -244,6 +257,10 @@ def test_train_step_end_to_end_report():
     cos = sorted(cosine(p.grad, ref_grads[k]) for k, p in model.named_parameters())
     print(f"train e2e: logits rel-L2 {e:.3e}, loss {loss.item():.5f} vs {ref_loss.item():.5f}, "
           f"grad cosine min {cos[0]:.4f} median {cos[len(cos) // 2]:.4f}")
+    record("test_train_step_end_to_end_report", logits_rel_l2_vs_fp32=e, loss=loss.item(), loss_oracle=ref_loss.item(),
+           grad_cos_min=cos[0], grad_cos_median=cos[len(cos) // 2],
+           note="bf16 train mode at random init is chaotic (SURVEY App. C: torch's own bf16 autocast vs fp32 gives "
+                "1.3e-1 / median cosine 0.94); reported, gated on sanity only")
     assert torch.isfinite(loss).item() and e < 0.5 and cos[len(cos) // 2] > 0.8
     assert abs(loss.item() - ref_loss.item()) < 0.1
 

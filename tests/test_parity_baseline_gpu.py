@@ -1,0 +1,282 @@
+"""Parity at the BASELINE sizes (BASELINE.json configs[1]-[4]).
+
+The per-module tests of test_modules_gpu.py run at 8^2-64^2; these run the shapes the benchmark runs:
+the 18 convolution layers of AttentionUNet(1,2,bilinear,64) at 512^2 input and batch 4 (plus the batch-32
+extremes), the gate and the decoder block at their real level shapes, the whole network in eval mode at
+4x1x512x512 against the fp32 oracle, and the batch-32 / batch-256 paths through self-consistency with the
+batch-4 run plus an oracle spot check.  Every measured number goes to the parity log
+(gpurun_out/r02_parity.json -> profiles/r02_parity.json).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import unet_oracle as O
+from parity_log import record
+from test_modules_gpu import _build, _x, check_module, cosine, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+# name, H (= W), C0, C1, Cout — the 3x3 convolutions of SURVEY App. B (inc.0 is the fp32 stem, tested apart)
+LAYERS = [
+    ("inc.3", 512, 64, 0, 64), ("down1.0", 256, 64, 0, 128), ("down1.3", 256, 128, 0, 128),
+    ("down2.0", 128, 128, 0, 256), ("down2.3", 128, 256, 0, 256), ("down3.0", 64, 256, 0, 512),
+    ("down3.3", 64, 512, 0, 512), ("down4.0", 32, 512, 0, 512), ("down4.3", 32, 512, 0, 512),
+    ("up1.0", 64, 512, 512, 512), ("up1.3", 64, 512, 0, 256), ("up2.0", 128, 256, 256, 256),
+    ("up2.3", 128, 256, 0, 128), ("up3.0", 256, 128, 128, 128), ("up3.3", 256, 128, 0, 64),
+    ("up4.0", 512, 64, 64, 64), ("up4.3", 512, 64, 0, 64),
+]
+# dispatcher expectation at these shapes (ub2_last_conv_variant): rows of >= 128 pixels and Cout <= 128 run the
+# halo-resident CTA-pair kernels, everything else the per-tap CTA-pair kernels
+def _expect(h, cout):
+    return (4, 14) if (h % 128 == 0 and cout <= 128) else (2, 12)
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+def _conv_case(name, n, h, c0, c1, cout):
+    from unet import kernels as K
+    cin = c0 + c1
+    x0 = _rand((n, h, h, c0), 1)
+    x1 = _rand((n, h, h, c1), 2) if c1 else None
+    wt = _rand((cout, cin, 3, 3), 3, scale=(9 * cin) ** -0.5)
+    dy = _rand((n, h, h, cout), 4)
+    xs = torch.cat([x0, x1], 3) if c1 else x0
+    x_nchw = xs.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    w32 = wt.float().requires_grad_(True)
+    # checker: fp32 convolution of the same bf16 operands (TF32 off), on the GPU for speed
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(x_nchw, w32, padding=1)
+        ref.backward(dy.float().permute(0, 3, 1, 2))
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    ref_y = ref.detach().permute(0, 2, 3, 1)
+    ref_dx = x_nchw.grad.permute(0, 2, 3, 1)
+    ref_dw = w32.grad
+
+    wf, wd = K.pack_conv_weight(wt.float().contiguous(), True, True)
+    y, st = K.conv_fwd(x0, wf, 9, x1=x1, stats=True)
+    v_fwd = K.last_conv_variant()
+    d0 = K.empty_nhwc(n, h, h, c0, "cuda")
+    d1 = K.empty_nhwc(n, h, h, c1, "cuda") if c1 else None
+    K.conv_fwd(dy, wd, 9, out=d0, out1=d1, split=c0)
+    v_dgrad = K.last_conv_variant()
+    part = K.conv_wgrad(x0, dy, 9, x1=x1)
+    v_wgrad = K.last_conv_variant()
+    dw = torch.empty(cout, cin, 3, 3, device="cuda")
+    K.wgrad_reduce(part, cout, cin, 9, dw)
+    dx = torch.cat([d0, d1], 3) if c1 else d0
+
+    def worst(got, ref_t):   # bf16 output of an fp32 accumulation: half an ulp of the result + order noise
+        err = (got.float() - ref_t).abs()
+        return (err / (2.0 ** -7 * ref_t.abs() + 2e-2 * ref_t.abs().mean())).max().item()
+
+    # batch statistics of the stored (bf16) values, as the epilogue reduces them
+    s = st.sum(0)
+    yf = y.float()
+    stat_err = max(((s[0] - yf.sum((0, 1, 2)).double()).abs().max() / yf.abs().sum((0, 1, 2)).double().max()).item(),
+                   ((s[1] - (yf.double() ** 2).sum((0, 1, 2))).abs().max() / (yf.double() ** 2).sum((0, 1, 2)).max()).item())
+    res = dict(shape=[n, h, h, c0, c1, cout], variant_fwd=v_fwd, variant_dgrad=v_dgrad, variant_wgrad=v_wgrad,
+               fwd_worst_err_over_tol=worst(y, ref_y), dgrad_worst_err_over_tol=worst(dx, ref_dx),
+               fwd_rel_l2=rel_l2(y, ref_y), dgrad_rel_l2=rel_l2(dx, ref_dx), wgrad_rel_l2=rel_l2(dw, ref_dw),
+               wgrad_cos=cosine(dw, ref_dw), stats_rel_err=stat_err)
+    record(f"conv[{name},N={n}]", **res)
+    return res
+
+
+def _check_conv(res, h, cout):
+    e_f, e_w = _expect(h, cout)
+    assert res["variant_fwd"] == e_f and res["variant_dgrad"] in (e_f, 2, 4), res
+    assert res["variant_wgrad"] in (e_w, 12, 13, 14), res
+    assert res["fwd_worst_err_over_tol"] <= 1.0 and res["dgrad_worst_err_over_tol"] <= 1.0, res
+    assert res["wgrad_rel_l2"] <= 2e-3 and res["stats_rel_err"] <= 1e-5, res
+
+
+@pytest.mark.parametrize("name,h,c0,c1,cout", LAYERS, ids=[l[0] for l in LAYERS])
+def test_conv_layer_shapes_batch4(name, h, c0, c1, cout):
+    _check_conv(_conv_case(name, 4, h, c0, c1, cout), h, cout)
+
+
+@pytest.mark.parametrize("name,h,c0,c1,cout", [l for l in LAYERS if l[0] in ("inc.3", "up4.0", "up1.0")],
+                         ids=["inc.3", "up4.0", "up1.0"])
+def test_conv_layer_shapes_batch32(name, h, c0, c1, cout):
+    _check_conv(_conv_case(name, 32, h, c0, c1, cout), h, cout)
+
+
+# --------------------------------------------------------------------------- modules at level shapes
+def test_gate_at_512_level():
+    """up4's gate: g (N,64,256,256), x (N,64,512,512), 32 inter-channels (layers.py:126-192)."""
+    from unet.models.layers import AttentionGate
+    check_module(AttentionGate(64, 64), lambda g, x, sd, tr: O.attention_gate(g, x, sd, "m", tr),
+                 [_x((1, 64, 256, 256), 41), _x((1, 64, 512, 512), 42)], True, tag="gate up4 @512 train")
+
+
+def test_gate_at_512_level_eval():
+    from unet.models.layers import AttentionGate
+    check_module(AttentionGate(64, 64), lambda g, x, sd, tr: O.attention_gate(g, x, sd, "m", tr),
+                 [_x((1, 64, 256, 256), 43), _x((1, 64, 512, 512), 44)], False, tag="gate up4 @512 eval")
+
+
+def test_attention_up_up1_shape():
+    """up1 = AttentionUp(1024, 256): x1 (N,512,32,32), skip (N,512,64,64)."""
+    from unet.models.layers import AttentionUp
+    check_module(AttentionUp(1024, 256, True),
+                 lambda x1, x2, sd, tr: O.up_block(x1, x2, sd, "m", True, True, tr),
+                 [_x((2, 512, 32, 32), 45), _x((2, 512, 64, 64), 46)], True, tag="AttentionUp up1 1024->256 @64 train")
+
+
+def test_attention_up_up4_shape():
+    """up4 = AttentionUp(128, 64): x1 (N,64,256,256), skip (N,64,512,512)."""
+    from unet.models.layers import AttentionUp
+    check_module(AttentionUp(128, 64, True),
+                 lambda x1, x2, sd, tr: O.up_block(x1, x2, sd, "m", True, True, tr),
+                 [_x((1, 64, 256, 256), 47), _x((1, 64, 512, 512), 48)], True, tag="AttentionUp up4 128->64 @512 train")
+
+
+def test_down1_shape():
+    from unet.models.layers import Down
+    check_module(Down(64, 128), lambda x, sd, tr: O.down(x, sd, "m", tr), [_x((2, 64, 512, 512), 49)], True,
+                 tag="Down down1 64->128 @512 train")
+
+
+# --------------------------------------------------------------------------- the whole network
+def _eval_logits(model, x, chunk=None):
+    model.eval()
+    with torch.no_grad():
+        return model(x.cuda())
+
+
+def test_eval_end_to_end_baseline_batch4():
+    """BASELINE configs[1] shape in eval mode: AttentionUNet(1,2,True,64), 4x1x512x512, bf16 path vs the
+    fp32 oracle: logits rel-L2 <= 2e-2, thresholded-mask agreement >= 99.9 %, confusion counts on
+    identical masks bit-exact (north_star tolerances)."""
+    from unet.utils.metrics import SegmentationMetrics
+    model, sd, _ = _build(True, 64, 42)
+    x, t = O.synthetic_batch(4, 512, 512, seed=1234)
+    logits = _eval_logits(model.cuda(), x)
+    ref = O.unet_forward(x, sd, attention=True, training=False)
+    e = rel_l2(logits, ref)
+    m_got = torch.softmax(logits.cpu(), 1)[:, 1] > 0.5
+    m_ref = torch.softmax(ref, 1)[:, 1] > 0.5
+    agree = (m_got == m_ref).float().mean().item()
+    arg_agree = (logits.cpu().argmax(1) == ref.argmax(1)).float().mean().item()
+    # metric confusion counts: on the SAME predicted masks the device histogram equals the reference loop's
+    m = SegmentationMetrics(2)
+    m.update(logits, t.cuda())
+    cm_ref = O.confusion_matrix(logits.cpu(), t, 2)
+    m2 = SegmentationMetrics(2)
+    m2.update(ref.argmax(1).cuda(), t.cuda())
+    cm_ref2 = O.confusion_matrix(ref.argmax(1), t, 2)
+    record("eval e2e AttentionUNet(1,2,True,64) 4x1x512x512 vs fp32 oracle", logits_rel_l2=e, mask_agreement=agree,
+           argmax_agreement=arg_agree, confusion_bit_exact=bool((m.confusion_matrix == cm_ref).all()),
+           confusion_on_oracle_masks_bit_exact=bool((m2.confusion_matrix == cm_ref2).all()),
+           confusion_matrix=m.confusion_matrix.tolist())
+    assert e <= 2e-2, f"eval logits rel-L2 {e:.3e}"
+    assert agree >= 0.999, f"mask agreement {agree:.5f}"
+    assert (m.confusion_matrix == cm_ref).all() and (m2.confusion_matrix == cm_ref2).all()
+
+
+def test_eval_batch256_equals_batch4_per_image():
+    """configs[4]'s largest batch: 256 images = the batch-4 input repeated 64 times.  Eval mode has no
+    cross-image term, so every image's logits must equal the batch-4 run's (the 2^32-element guards and
+    the multi-tile persistent loops are what is exercised); images 0 and 255 are also checked against the
+    fp32 oracle."""
+    model, sd, _ = _build(True, 64, 42)
+    model = model.cuda()
+    x4, _ = O.synthetic_batch(4, 512, 512, seed=1234)
+    ref4 = _eval_logits(model, x4)
+    big = _eval_logits(model, x4.repeat(64, 1, 1, 1))
+    assert big.shape == (256, 2, 512, 512)
+    worst, exact = 0.0, 0
+    for i in range(256):
+        d = (big[i] - ref4[i % 4]).abs().max().item()
+        worst = max(worst, d)
+        exact += int(d == 0.0)
+    spot = O.unet_forward(x4[[0, 3]], sd, attention=True, training=False)
+    e0 = rel_l2(big[0:1], spot[0:1])
+    e255 = rel_l2(big[255:256], spot[1:2])
+    record("eval batch 256 vs batch 4 (same images)", max_abs_diff=worst, images_bit_identical=exact,
+           oracle_rel_l2_image0=e0, oracle_rel_l2_image255=e255, logits_abs_max=ref4.abs().max().item())
+    assert worst <= 1e-3 * ref4.abs().max().item()
+    assert e0 <= 2e-2 and e255 <= 2e-2
+    del big
+    torch.cuda.empty_cache()
+
+
+def test_eval_batch32_unet_equals_batch4_per_image():
+    """Plain UNet (configs[2]'s model) at batch 32, eval: same check."""
+    model, sd, _ = _build(False, 64, 43)
+    model = model.cuda()
+    x4, _ = O.synthetic_batch(4, 512, 512, seed=77)
+    ref4 = _eval_logits(model, x4)
+    big = _eval_logits(model, x4.repeat(8, 1, 1, 1))
+    worst = max((big[i] - ref4[i % 4]).abs().max().item() for i in range(32))
+    spot = O.unet_forward(x4[:1], sd, attention=False, training=False)
+    e0 = rel_l2(big[28:29], spot)
+    record("UNet eval batch 32 vs batch 4 (same images)", max_abs_diff=worst, oracle_rel_l2_image28=e0)
+    assert worst <= 1e-3 * ref4.abs().max().item() and e0 <= 2e-2
+
+
+def test_train_batch32_equals_batch4_statistics_and_gradients():
+    """configs[3]'s per-GPU batch in TRAIN mode: 32 images = the batch-4 input repeated 8 times.  Batch
+    statistics of the repeated batch equal the batch-4 statistics, and DiceBCE is a mean of per-image
+    terms, so logits repeat and every parameter gradient equals the batch-4 gradient up to summation
+    order; bf16 rounding of the statistics' consumers is identical on both sides."""
+    from unet.models import AttentionUNet
+    from unet.utils.loss import DiceBCELoss
+    x4, t4 = O.synthetic_batch(4, 512, 512, seed=1234)
+    out = {}
+    for reps in (1, 8):
+        torch.manual_seed(42)
+        model = AttentionUNet(1, 2, True, 64).cuda().train()
+        x, t = x4.repeat(reps, 1, 1, 1).cuda(), t4.repeat(reps, 1, 1).cuda()
+        logits = model(x)
+        loss = DiceBCELoss()(logits, t)
+        loss.backward()
+        out[reps] = (logits.detach()[:4].clone(), loss.item(), {k: p.grad.clone() for k, p in model.named_parameters()},
+                     model.inc.double_conv[1].running_mean.clone())
+        del model, logits, loss
+        torch.cuda.empty_cache()
+    (l4, loss4, g4, rm4), (l32, loss32, g32, rm32) = out[1], out[8]
+    e = rel_l2(l32, l4)
+    cos = {k: cosine(g32[k], g4[k]) for k in g4}
+    ratio = {k: (g32[k].norm() / (g4[k].norm() + 1e-30)).item() for k in g4}
+    worst = min(cos, key=cos.get)
+    record("train batch 32 (4 images x 8) vs batch 4", logits_rel_l2=e, loss_b4=loss4, loss_b32=loss32,
+           grad_cos_min=cos[worst], grad_cos_min_param=worst, grad_cos_median=sorted(cos.values())[len(cos) // 2],
+           grad_norm_ratio_min=min(ratio.values()), grad_norm_ratio_max=max(ratio.values()),
+           running_mean_max_abs_diff=(rm4 - rm32).abs().max().item())
+    # The repeated batch has the same statistics only up to summation order, and train-mode bf16 at random init
+    # amplifies any perturbation (1.3e-5 logits from 1e-7 order noise in fp32; bf16 re-rounding of
+    # an activation that moved by one ulp is 2^-8): gates are loose on logits, tight on the loss and the buffers
+    assert abs(loss4 - loss32) <= 2e-3 * abs(loss4)
+    assert torch.allclose(rm4, rm32, rtol=1e-3, atol=1e-5)
+    assert e <= 5e-2 and sorted(cos.values())[len(cos) // 2] >= 0.99
+
+
+def test_train_step_baseline_batch4_loss_and_first_layer_gradients():
+    """configs[1] itself, one train step at 4x1x512x512 against the fp32 oracle's train step: loss, logits
+    and per-parameter gradient cosines are REPORTED beside the noise floor of SURVEY App. C (bf16 train mode
+    at random init is chaotic end to end); gated on the loss and on sanity."""
+    from unet.utils.loss import DiceBCELoss
+    model, sd, _ = _build(True, 64, 42)
+    x, t = O.synthetic_batch(4, 512, 512, seed=1234)
+    model = model.cuda().train()
+    logits = model(x.cuda())
+    loss = DiceBCELoss()(logits, t.cuda())
+    loss.backward()
+    ref_loss, ref_logits, ref_grads = O.train_grads(x, t, O.clone_state(sd), attention=True)
+    e = rel_l2(logits, ref_logits)
+    cos = {k: cosine(p.grad, ref_grads[k]) for k, p in model.named_parameters()}
+    srt = sorted(cos.values())
+    record("train step AttentionUNet(1,2,True,64) 4x1x512x512 vs fp32 oracle", logits_rel_l2=e, loss=loss.item(),
+           loss_oracle=ref_loss.item(), grad_cos_min=srt[0], grad_cos_median=srt[len(srt) // 2],
+           grad_cos_p10=srt[len(srt) // 10], grad_cos_per_param={k: round(v, 5) for k, v in cos.items()},
+           floor="SURVEY App. C: torch bf16 autocast vs fp32 train mode = logits 1.3e-1, mask 95.8 %")
+    assert abs(loss.item() - ref_loss.item()) <= 5e-2 * abs(ref_loss.item())
+    assert e < 0.5 and srt[len(srt) // 2] > 0.8

@@ -42,6 +42,31 @@ def _digest(path: str) -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines) -> str:
+    """A second build of the same sources with extra -D flags, as lib/libunetb200.<name>.so — for same-box
+    A/B runs of a kernel change (select it with UB2_LIB=<path>, see unet/_C.py and tools/ab_lib.sh)."""
+    objdir = os.path.join(OBJDIR, name)
+    os.makedirs(objdir, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, f"libunetb200.{name}.so")
+    flags = FLAGS + [f"-D{d}" for d in defines]
+
+    def one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        r = subprocess.run([NVCC, *flags, "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(one, _sources()))
+    r = subprocess.run([NVCC, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
@@ -78,4 +103,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:   # python build.py --variant <name> DEFINE [DEFINE ...]
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

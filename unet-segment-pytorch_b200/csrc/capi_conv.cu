@@ -46,6 +46,8 @@ int ub2_conv_wgrad(const void* in0, int ld_in0, int C0, const void* in1, int ld_
 
 int ub2_num_sms(void) { return num_sms(); }
 
+int ub2_last_conv_variant(void) { return last_variant(); }
+
 int ub2_set_conv_mode(int mode) {
   conv_set_mode(mode);
   return 0;

@@ -86,6 +86,11 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C,
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
                  uint32_t bc, uint32_t br, int swizzle_bytes, int elem_bytes = 2);
 int num_sms();
+// Which kernel the dispatcher picked for the calling thread's last convolution launch (tests assert it):
+// forward / dgrad 1 = conv_fwd (one CTA, per tap), 2 = conv_fwd2 (CTA pair, per tap), 3 = conv_halo (one CTA,
+// halo resident), 4 = conv_halo2 (CTA pair, halo resident); weight gradient 11..14 likewise.
+void note_variant(int code);
+int last_variant();
 // Launch state that is per device (function attributes and occupancy belong to a context, and two B200s
 // of one box need not have the same number of complete TPCs): every `static` cache of the launchers is
 // one slot per device ordinal.  Slots hold idempotent results, so a racing first use by two host

@@ -339,6 +339,7 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   }
   // running-sum statistics need one 32-column chunk per epilogue warp and a single N tile
   const bool acc = a.stats != nullptr && bn_cols <= 64 && p.n_tiles == 1;
+  note_variant(1);
   if (a.tf32) {
     if (a.taps == 9) conv_fwd_kernel<9, false, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
     else conv_fwd_kernel<1, false, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);

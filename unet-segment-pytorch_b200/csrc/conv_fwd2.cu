@@ -317,10 +317,10 @@ int conv_fwd2_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   if (a.stats && grid > a.stats_rows) return UB2_ERR_WORKSPACE;
   const size_t smem = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(Fwd2SmemHeader) + stats_bytes;
   switch (variant) {
-    case 0: conv_fwd2_kernel<9, false><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
-    case 1: conv_fwd2_kernel<9, true><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
-    case 2: conv_fwd2_kernel<1, false><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
-    default: conv_fwd2_kernel<1, true><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
+    case 0: note_variant(2); conv_fwd2_kernel<9, false><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
+    case 1: note_variant(2); conv_fwd2_kernel<9, true><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
+    case 2: note_variant(2); conv_fwd2_kernel<1, false><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
+    default: note_variant(2); conv_fwd2_kernel<1, true><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -319,6 +319,7 @@ int conv_halo_launch(const ConvFwdArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   const bool acc = a.stats != nullptr && bn_cols <= 64 && p.n_tiles == 1;
+  note_variant(3);
   if (acc) conv_halo_kernel<true><<<grid, kHThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
   else conv_halo_kernel<false><<<grid, kHThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
   cudaError_t e = cudaGetLastError();

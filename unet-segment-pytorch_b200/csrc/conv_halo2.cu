@@ -348,6 +348,7 @@ int conv_halo2_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   if (clusters > pairs) clusters = pairs;
   const int grid = 2 * clusters;
   if (a.stats && grid > a.stats_rows) return UB2_ERR_WORKSPACE;
+  note_variant(4);
   if (acc) conv_halo2_kernel<true><<<grid, kH2Threads, smem, stream>>>(tmA0, tmA1, tmB, p);
   else conv_halo2_kernel<false><<<grid, kH2Threads, smem, stream>>>(tmA0, tmA1, tmB, p);
   cudaError_t e = cudaGetLastError();

@@ -315,6 +315,7 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
+  note_variant(11);
   conv_wgrad_kernel<<<grid, kWThreads, smem, stream>>>(tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -325,6 +325,7 @@ int conv_wgrad2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   const int total_items = tiles * splits;
   const int grid = 2 * (max_clusters < total_items ? max_clusters : total_items);
   const size_t smem = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(Wg2SmemHeader);
+  note_variant(12);
   conv_wgrad2_kernel<<<grid, kW2Threads, smem, stream>>>(tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -304,6 +304,7 @@ int conv_wgrad_halo_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
+  note_variant(13);
   conv_wgrad_halo_kernel<<<grid, kGThreads, smem, stream>>>(tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -352,6 +352,7 @@ int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   const int grid = 2 * (items < max_clusters ? items : max_clusters);
   const size_t smem = 1024 + 2 * static_cast<size_t>(p.a_bytes) + static_cast<size_t>(b_stages) * p.b_stage_bytes +
                       sizeof(WgHalo2Header);
+  note_variant(14);
   conv_wgrad_halo2_kernel<<<grid, kG2Threads, smem, stream>>>(tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);

@@ -67,6 +67,10 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows,
   return r == CUDA_SUCCESS ? 0 : UB2_ERR_DRIVER;
 }
 
+static thread_local int g_variant = 0;
+void note_variant(int code) { g_variant = code; }
+int last_variant() { return g_variant; }
+
 int device_index() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) {

@@ -20,8 +20,11 @@ F32 = torch.float32
 F64 = torch.float64
 
 _SMS = None
-# When set to a list, conv_fwd appends (start_event, end_event, algorithmic_flops) per launch.
-PROFILE = None
+
+
+def _nbytes(*tensors) -> int:
+    """Algorithmic bytes of a bandwidth-bound call: every tensor it reads or writes, touched once."""
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
 
 
 def num_sms() -> int:
@@ -29,6 +32,11 @@ def num_sms() -> int:
     if _SMS is None:
         _SMS = int(_C.lib().ub2_num_sms())
     return _SMS
+
+
+def last_conv_variant() -> int:
+    """Kernel the dispatcher picked for this thread's last conv_fwd / conv_wgrad (see unetb200.h)."""
+    return int(_C.lib().ub2_last_conv_variant())
 
 
 def _nhwc(t: torch.Tensor):
@@ -80,16 +88,10 @@ def conv_fwd(x0, wgt, taps, x1=None, out=None, out1=None, split=0, scale=None, s
         rows = num_sms()
         st = torch.empty((rows, 2, cout), device=x0.device, dtype=F64)
     used = c_int(0)
-    prof = PROFILE
-    if prof is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
     _C.call("ub2_conv_fwd", ptr(x0), ld0_in, c0, ptr(x1), ld1_in, c1, ptr(wgt), ptr(out), ldo0,
             ptr(out1), ldo1, split, n, h, w, cout, taps, ptr(scale), ptr(shift), int(relu),
-            int(accumulate), ptr(st), rows, byref(used), bn_override, grid_override, stream())
-    if prof is not None:
-        e1.record()
-        prof.append((e0, e1, 2.0 * n * h * w * cout * taps * (c0 + c1)))
+            int(accumulate), ptr(st), rows, byref(used), bn_override, grid_override, stream(),
+            work=(2.0 * n * h * w * cout * taps * (c0 + c1), _nbytes(x0, x1, wgt, out, out1)))
     if stats:
         return out, st[: used.value]
     return out
@@ -108,7 +110,8 @@ def conv_wgrad(x0, dy, taps, x1=None, splits_override=0):
     partial = torch.empty((max_splits, mtot, cout), device=x0.device, dtype=F32)
     used = c_int(0)
     _C.call("ub2_conv_wgrad", ptr(x0), ld0_in, c0, ptr(x1), ld1_in, c1, ptr(dy), ld_dy,
-            ptr(partial), max_splits, byref(used), n, h, w, cout, taps, splits_override, stream())
+            ptr(partial), max_splits, byref(used), n, h, w, cout, taps, splits_override, stream(),
+            work=(2.0 * n * h * w * cout * mtot, _nbytes(x0, x1, dy) + 4 * mtot * cout))
     return partial[: used.value]
 
 
@@ -216,7 +219,7 @@ def bn_act(y, scale, shift, relu=True, pool=False, write_act=True, want_idx=Fals
     p = empty_nhwc(n, h // 2, w // 2, c, y.device) if pool else None
     idx = torch.empty((n, h // 2, w // 2, c), device=y.device, dtype=torch.uint8) if pool and want_idx else None
     _C.call("ub2_bn_act", ptr(y), ld, ptr(scale), ptr(shift), ptr(a), c, ptr(p), c, ptr(idx), n, h, w, c,
-            int(relu), stream())
+            int(relu), stream(), work=(0.0, _nbytes(y, a, p, idx)))
     if want_idx:
         return a, p, idx
     return a, p
@@ -235,11 +238,12 @@ def bn_backward(dA, dP, pidx, y, scale, shift, mean, invstd, gamma, relu=True, f
     dev = y.device
     partials = torch.empty((rows, 2, c), device=dev, dtype=F64)
     _C.call("ub2_bn_bwd_reduce", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(pidx), ptr(y), ld_y, ptr(scale),
-            ptr(shift), ptr(partials), rows, n, h, w, c, int(relu), stream())
+            ptr(shift), ptr(partials), rows, n, h, w, c, int(relu), stream(), work=(0.0, _nbytes(dA, dP, pidx, y)))
     dgamma, dbeta, coef = bn_bwd_finalize(partials, n * h * w, gamma, mean, invstd, frozen, dgamma, dbeta)
     dy = empty_nhwc(n, h, w, c, dev)
     _C.call("ub2_bn_bwd_apply", ptr(dA), ld_da, ptr(dP), ld_dp, ptr(pidx), ptr(y), ld_y, ptr(scale),
-            ptr(shift), ptr(coef), ptr(dy), c, n, h, w, c, int(relu), stream())
+            ptr(shift), ptr(coef), ptr(dy), c, n, h, w, c, int(relu), stream(),
+            work=(0.0, _nbytes(dA, dP, pidx, y, dy)))
     return dy, dgamma, dbeta
 
 
@@ -276,7 +280,8 @@ def maxpool_bwd(dP, pidx, a):
 def upsample(x, hu, wu, ho, wo):
     n, hin, win, c, ld = _nhwc(x)
     out = empty_nhwc(n, ho, wo, c, x.device)
-    _C.call("ub2_upsample_fwd", ptr(x), ld, ptr(out), c, n, hin, win, hu, wu, ho, wo, c, stream())
+    _C.call("ub2_upsample_fwd", ptr(x), ld, ptr(out), c, n, hin, win, hu, wu, ho, wo, c, stream(),
+            work=(0.0, _nbytes(x, out)))
     return out
 
 
@@ -285,7 +290,7 @@ def upsample_bwd(dout, hin, win, hu, wu, into=None):
     acc = into is not None
     din = into if acc else empty_nhwc(n, hin, win, c, dout.device)
     _C.call("ub2_upsample_bwd", ptr(dout), ld, ptr(din), _nhwc(din)[4], int(acc), n, hin, win, hu, wu,
-            ho, wo, c, stream())
+            ho, wo, c, stream(), work=(0.0, _nbytes(dout, din) * (2 if acc else 1) - (_nbytes(dout) if acc else 0)))
     return din
 
 
@@ -302,7 +307,8 @@ def gate_upstats(q, h, w):
     n, hin, win, ci, ld = _nhwc(q)
     rows = gate_strip_rows(n, h, w, ci)
     partials = torch.empty((rows, 2, ci), device=q.device, dtype=F64)
-    _C.call("ub2_gate_upstats", ptr(q), ld, n, hin, win, h, w, ci, ptr(partials), rows, stream())
+    _C.call("ub2_gate_upstats", ptr(q), ld, n, hin, win, h, w, ci, ptr(partials), rows, stream(),
+            work=(0.0, _nbytes(q)))
     return partials
 
 
@@ -313,7 +319,7 @@ def gate_psi(q, xp, sg, hg, sx, hx, wpsi, stats=True):
     rows = gate_strip_rows(n, h, w, ci)
     partials = torch.empty((rows, 2, 1), device=q.device, dtype=F64) if stats else None
     _C.call("ub2_gate_psi", ptr(q), ld_q, ptr(xp), ld_xp, ptr(sg), ptr(hg), ptr(sx), ptr(hx), ptr(wpsi),
-            ptr(psi), ptr(partials), rows, n, hin, win, h, w, ci, stream())
+            ptr(psi), ptr(partials), rows, n, hin, win, h, w, ci, stream(), work=(0.0, _nbytes(q, xp, psi)))
     return psi, partials
 
 
@@ -322,7 +328,7 @@ def gate_apply(psi, spsi, hpsi, x, save_a=True):
     out = empty_nhwc(n, h, w, cx, x.device)
     a = torch.empty((n, h, w), device=x.device, dtype=F32) if save_a else None
     _C.call("ub2_gate_apply", ptr(psi), ptr(spsi), ptr(hpsi), ptr(x), ld, ptr(out), cx, ptr(a), n, h, w,
-            cx, stream())
+            cx, stream(), work=(0.0, _nbytes(psi, x, out, a)))
     return out, a
 
 
@@ -334,7 +340,7 @@ def gate_bwd_a(dout, x, a, psi):
     rows = gate_rows(n, h, w, cx)
     partials = torch.empty((rows, 2, 1), device=x.device, dtype=F64)
     _C.call("ub2_gate_bwd_a", ptr(dout), ld_do, ptr(x), ld_x, ptr(a), ptr(psi), ptr(dx), cx, ptr(dpsin),
-            ptr(partials), rows, n, h, w, cx, stream())
+            ptr(partials), rows, n, h, w, cx, stream(), work=(0.0, _nbytes(dout, x, a, psi, dx, dpsin)))
     return dx, dpsin, partials
 
 
@@ -346,7 +352,7 @@ def gate_bwd_s(dpsin, psi, coef_psi, q, xp, sg, hg, sx, hx, wpsi):
     partials = torch.empty((rows, 4, ci), device=q.device, dtype=F64)
     _C.call("ub2_gate_bwd_s", ptr(dpsin), ptr(psi), ptr(coef_psi), ptr(q), ld_q, ptr(xp), ld_xp, ptr(sg),
             ptr(hg), ptr(sx), ptr(hx), ptr(wpsi), ptr(ds), ci, ptr(partials), rows, n, hin, win, h, w, ci,
-            stream())
+            stream(), work=(0.0, _nbytes(dpsin, psi, q, xp, ds)))
     return ds, partials
 
 
@@ -371,7 +377,7 @@ def gate_bwd_xg(ds, xp, q, coef):
     dxp = empty_nhwc(n, h, w, ci, q.device)
     dgup = empty_nhwc(n, h, w, ci, q.device)
     _C.call("ub2_gate_bwd_xg", ptr(ds), _nhwc(ds)[4], ptr(xp), ld_xp, ptr(q), ld_q, ptr(coef), ptr(dxp), ci,
-            ptr(dgup), ci, n, hin, win, h, w, ci, stream())
+            ptr(dgup), ci, n, hin, win, h, w, ci, stream(), work=(0.0, _nbytes(ds, xp, q, dxp, dgup)))
     return dxp, dgup
 
 
@@ -385,7 +391,7 @@ def conv_in_fwd(x, w, stats=True):
     rows = _rows("ub2_conv_in_rows", n, h, wd, cout)
     partials = torch.empty((rows, 2, cout), device=x.device, dtype=F64) if stats else None
     _C.call("ub2_conv_in_fwd", ptr(x), ptr(w), ptr(y), cout, ptr(partials), rows, n, cin, h, wd, cout,
-            stream())
+            stream(), work=(2.0 * n * h * wd * cout * 9 * cin, _nbytes(x, y)))
     return y, partials
 
 
@@ -397,7 +403,7 @@ def conv_in_wgrad(x, dy, cout, grad=None):
     if grad is None:
         grad = torch.zeros((cout, cin, 3, 3), device=x.device, dtype=F32)
     _C.call("ub2_conv_in_wgrad", ptr(x), ptr(dy), _nhwc(dy)[4], ptr(partials), rows, ptr(grad), n, cin,
-            h, wd, cout, stream())
+            h, wd, cout, stream(), work=(2.0 * n * h * wd * cout * 9 * cin, _nbytes(x, dy)))
     return grad
 
 
@@ -405,7 +411,8 @@ def outc_fwd(a, w, bias):
     n, h, wd, c, ld = _nhwc(a)
     k = w.shape[0]
     logits = torch.empty((n, k, h, wd), device=a.device, dtype=F32)
-    _C.call("ub2_outc_fwd", ptr(a), ld, ptr(w), ptr(bias), ptr(logits), n, h, wd, c, k, stream())
+    _C.call("ub2_outc_fwd", ptr(a), ld, ptr(w), ptr(bias), ptr(logits), n, h, wd, c, k, stream(),
+            work=(0.0, _nbytes(a, logits)))
     return logits
 
 
@@ -422,7 +429,7 @@ def outc_bwd(dlogits, a, w, need_da=True, dw=None, db=None):
     if db is None:
         db = torch.zeros((k,), device=a.device, dtype=F32)
     _C.call("ub2_outc_bwd", ptr(dlogits), ptr(a), ld, ptr(w), ptr(da), c, ptr(partials), rows, ptr(dw),
-            ptr(db), n, h, wd, c, k, stream())
+            ptr(db), n, h, wd, c, k, stream(), work=(0.0, _nbytes(dlogits, a, da)))
     return da, dw, db
 
 
@@ -436,7 +443,7 @@ def seg_stats(logits, targets):
     partials = torch.empty((n, blocks, c, 4), device=logits.device, dtype=F64)
     stats = torch.empty((n, 4, c), device=logits.device, dtype=F32)
     _C.call("ub2_seg_stats", ptr(logits), ptr(targets), n, c, c_longlong(h * w), ptr(partials), blocks,
-            ptr(stats), stream())
+            ptr(stats), stream(), work=(0.0, _nbytes(logits, targets)))
     return stats
 
 
@@ -449,7 +456,7 @@ def seg_stats_bwd(logits, targets, coef, gscale=None):
     assert gscale is None or (gscale.dtype == F32 and gscale.numel() == 1)
     dl = torch.empty_like(logits)
     _C.call("ub2_seg_stats_bwd", ptr(logits), ptr(targets.contiguous()), ptr(coef), ptr(gscale), n, c,
-            c_longlong(h * w), ptr(dl), stream())
+            c_longlong(h * w), ptr(dl), stream(), work=(0.0, _nbytes(logits, targets, dl)))
     return dl
 
 
@@ -480,7 +487,7 @@ def confusion(pred, target, num_classes, cm, ignore_index=None, threshold=None, 
     _C.call("ub2_confusion", ptr(pred), ptr(target), mode, n, num_classes, c_longlong(h * w),
             c_longlong(ignore_index if ignore_index is not None else 0),
             int(ignore_index is not None), c_float(threshold if threshold is not None else 0.5), ptr(cm),
-            ptr(mask_out), stream())
+            ptr(mask_out), stream(), work=(0.0, _nbytes(pred, target, mask_out)))
     return cm
 
 
