@@ -112,15 +112,33 @@ def check_module(module, oracle_fn, inputs, training, seed=0, input_needs_grad=T
                 problems.append(f"input {i} grad cosine vs fp32 oracle {c:.5f}")
             if e > 2e-2:
                 problems.append(f"input {i} grad rel-L2 vs bf16-model oracle {e:.3e}")
-    for name, p in cuda_mod.named_parameters():
-        r, r2 = ref_par["m." + name], st_par["m." + name]
-        if r is None or r.norm() == 0:
+    # A BatchNorm2d(1) (the gate's psi.1) has one-element weight / bias gradients: a cosine is +-1 and the
+    # bias gradient is a plain sum of signed per-pixel terms that nearly cancels under white-noise upstream
+    # gradients, so its relative error is unbounded.  Such pairs are compared as ONE vector (dgamma, dbeta).
+    named = dict(cuda_mod.named_parameters())
+    groups = []
+    for name, p in named.items():
+        if p.numel() == 1 and name.endswith(".weight") and name[:-6] + "bias" in named and named[name[:-6] + "bias"].numel() == 1:
+            groups.append((name[:-7] + ".{weight,bias}", [name, name[:-6] + "bias"]))
+        elif p.numel() == 1 and name.endswith(".bias") and name[:-4] + "weight" in named and named[name[:-4] + "weight"].numel() == 1:
             continue
-        c, c2 = cosine(p.grad, r), cosine(p.grad, r2)
-        scale = (p.grad.float().cpu().norm() / r2.norm()).item()
+        else:
+            groups.append((name, [name]))
+    for name, members in groups:
+        if any(ref_par["m." + m] is None for m in members):
+            continue
+        got = torch.cat([named[m].grad.detach().float().cpu().flatten() for m in members])
+        r = torch.cat([ref_par["m." + m].flatten() for m in members])
+        r2 = torch.cat([st_par["m." + m].flatten() for m in members])
+        if r.norm() == 0:
+            continue
+        c, c2 = cosine(got, r), cosine(got, r2)
+        scale = (got.norm() / r2.norm()).item()
         report.append(f"{name}: cos fp32 {c:.5f} bf16-model {c2:.5f} norm ratio {scale:.4f}")
         log[f"grad {name}"] = {"cos_vs_fp32": c, "cos_vs_bf16_model": c2, "cos_floor_bf16_model_vs_fp32": cosine(r2, r),
                                "norm_ratio": scale}
+        if len(members) > 1:
+            log[f"grad {name}"]["values"] = {"got": got.tolist(), "bf16_model": r2.tolist(), "fp32": r.tolist()}
         if c < 0.995:
             problems.append(f"{name}: grad cosine vs fp32 {c:.5f}")
         if c2 < 0.999:
