@@ -12,6 +12,7 @@
 //
 // Threads walk 2x2 pixel windows x 8-channel (128-bit) vectors; a thread's channel
 // group is fixed so per-channel coefficients live in registers.
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "vec.cuh"
@@ -27,6 +28,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partials, int rows
                                    float* running_mean, float* running_var, long long* nbt,
                                    float momentum, float eps, float* scale, float* shift, float* mean,
                                    float* invstd) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double smem[2 * 128 * 9];
   const int c = blockIdx.x * 8 + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && nbt != nullptr) *nbt += 1;
@@ -53,6 +56,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partials, int rows
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rm, const float* __restrict__ rv,
                                       float eps, int C, float* scale, float* shift) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float inv = 1.f / sqrtf(rv[c] + eps);
@@ -83,6 +88,8 @@ __global__ void __launch_bounds__(kBnThreads, 4)
 bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __restrict__ scale,
               const float* __restrict__ shift, __nv_bfloat16* a, int ld_a, __nv_bfloat16* pooled,
               int ld_p, unsigned char* pidx, int relu, WinGeom g) {
+  pdl_trigger();
+  pdl_wait();
   const int lanes = blockDim.x / g.cgs;
   const int lane = threadIdx.x / g.cgs;
   const int cg = threadIdx.x % g.cgs;
@@ -172,6 +179,8 @@ struct BwdArgs {
 template <bool POOL, bool APPLY>
 __global__ void __launch_bounds__(kBnThreads, 2)
 bn_bwd_kernel(BwdArgs a, WinGeom g) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_red[];
   const int lanes = blockDim.x / g.cgs;
   const int lane = threadIdx.x / g.cgs;
@@ -300,6 +309,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partials, int 
                                        double count, const float* __restrict__ gamma,
                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                        int frozen, float* dgamma, float* dbeta, float* coef) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double smem[2 * 128 * 9];
   const int c = blockIdx.x * 8 + threadIdx.x;
   double s[2];
@@ -332,9 +343,7 @@ int ub2_bn_finalize(const double* partials, int rows, int C, double count, const
                     float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
                     void* stream) {
   if (C <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  bn_finalize_kernel<<<(C + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream)>>>(
-      partials, rows, C, count, gamma, beta, running_mean, running_var, nbt, momentum, eps, scale,
-      shift, mean, invstd);
+  launch(bn_finalize_kernel, (C + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream), partials, rows, C, count, gamma, beta, running_mean, running_var, nbt, momentum, eps, scale, shift, mean, invstd);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -342,8 +351,7 @@ int ub2_bn_eval_coeffs(const float* gamma, const float* beta, const float* runni
                        const float* running_var, float eps, int C, float* scale, float* shift,
                        void* stream) {
   if (C <= 0) return UB2_ERR_SHAPE;
-  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      gamma, beta, running_mean, running_var, eps, C, scale, shift);
+  launch(bn_eval_coeffs_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), gamma, beta, running_mean, running_var, eps, C, scale, shift);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -357,9 +365,7 @@ int ub2_bn_act(const void* y, int ld_y, const float* scale, const float* shift, 
   const int block = bn_block(g.cgs);
   const int lanes = block / g.cgs;
   const int grid = stream_grid(g.windows, lanes, num_sms(), 8);
-  bn_act_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, static_cast<__nv_bfloat16*>(a), ld_a,
-      static_cast<__nv_bfloat16*>(pooled), ld_p, pidx, relu, g);
+  launch(bn_act_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, static_cast<__nv_bfloat16*>(a), ld_a, static_cast<__nv_bfloat16*>(pooled), ld_p, pidx, relu, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -390,8 +396,8 @@ int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, cons
   BwdArgs a{static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp, pidx,
             static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, nullptr, nullptr, 0, partials, relu};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (pool) bn_bwd_kernel<true, false><<<grid, block, smem, s>>>(a, g);
-  else bn_bwd_kernel<false, false><<<grid, block, smem, s>>>(a, g);
+  if (pool) launch(bn_bwd_kernel<true, false>, grid, block, smem, s, a, g);
+  else launch(bn_bwd_kernel<false, false>, grid, block, smem, s, a, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -399,8 +405,7 @@ int ub2_bn_bwd_finalize(const double* partials, int rows, int C, double count, c
                         const float* mean, const float* invstd, int frozen, float* dgamma, float* dbeta,
                         float* coef, void* stream) {
   if (C <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream)>>>(
-      partials, rows, C, count, gamma, mean, invstd, frozen, dgamma, dbeta, coef);
+  launch(bn_bwd_finalize_kernel, (C + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream), partials, rows, C, count, gamma, mean, invstd, frozen, dgamma, dbeta, coef);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -419,8 +424,8 @@ int ub2_bn_bwd_apply(const void* dA, int ld_da, const void* dP, int ld_dp, const
             static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, coef,
             static_cast<__nv_bfloat16*>(dY), ld_dy, nullptr, relu};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (pool) bn_bwd_kernel<true, true><<<grid, block, 0, s>>>(a, g);
-  else bn_bwd_kernel<false, true><<<grid, block, 0, s>>>(a, g);
+  if (pool) launch(bn_bwd_kernel<true, true>, grid, block, 0, s, a, g);
+  else launch(bn_bwd_kernel<false, true>, grid, block, 0, s, a, g);
   return static_cast<int>(cudaGetLastError());
 }
 

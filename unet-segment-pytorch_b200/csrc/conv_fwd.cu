@@ -16,6 +16,7 @@
 // inference), optional accumulate into the destination, bf16 store, and
 // per-channel sum / sum-of-squares of the rounded outputs (BatchNorm batch
 // statistics, layers.py:33) reduced with a register butterfly.
+#include "launch.cuh"
 #include <cstdlib>
 #include "conv.h"
 #include "conv_epilogue.cuh"
@@ -44,6 +45,7 @@ template <int TAPS, bool ACC, bool TF32>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const ConvFwdParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-align the tile ring (128B swizzle atoms repeat every 1024 B).
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -87,6 +89,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();   // the prologue above touched no global memory; everything below may (launch.cuh)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -341,14 +344,14 @@ int conv_fwd_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   const bool acc = a.stats != nullptr && bn_cols <= 64 && p.n_tiles == 1;
   note_variant(1);
   if (a.tf32) {
-    if (a.taps == 9) conv_fwd_kernel<9, false, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
-    else conv_fwd_kernel<1, false, true><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+    if (a.taps == 9) launch(conv_fwd_kernel<9, false, true>, grid, kThreads, smem, stream, tmA0, tmA1, tmB, p);
+    else launch(conv_fwd_kernel<1, false, true>, grid, kThreads, smem, stream, tmA0, tmA1, tmB, p);
   } else if (a.taps == 9) {
-    if (acc) conv_fwd_kernel<9, true, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
-    else conv_fwd_kernel<9, false, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+    if (acc) launch(conv_fwd_kernel<9, true, false>, grid, kThreads, smem, stream, tmA0, tmA1, tmB, p);
+    else launch(conv_fwd_kernel<9, false, false>, grid, kThreads, smem, stream, tmA0, tmA1, tmB, p);
   } else {
-    if (acc) conv_fwd_kernel<1, true, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
-    else conv_fwd_kernel<1, false, false><<<grid, kThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+    if (acc) launch(conv_fwd_kernel<1, true, false>, grid, kThreads, smem, stream, tmA0, tmA1, tmB, p);
+    else launch(conv_fwd_kernel<1, false, false>, grid, kThreads, smem, stream, tmA0, tmA1, tmB, p);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);

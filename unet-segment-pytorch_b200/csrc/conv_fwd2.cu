@@ -5,6 +5,7 @@
 // 16 + <=32 KB), one tcgen05.mma.cta_group::2 (M = 256) feeds both accumulators.  At batch 4 the
 // deep layers are L2 -> shared-memory bound in the one-CTA kernel.  bf16, 3x3, 64-channel chunks.
 // Barrier protocol as in conv_halo2.cu.
+#include "launch.cuh"
 #include <cstdlib>
 #include "conv.h"
 #include "conv_epilogue.cuh"
@@ -32,6 +33,7 @@ template <int TAPS, bool ACC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kF2Threads, 1)
 conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const ConvFwdParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -80,6 +82,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();   // the prologue above touched no global memory; everything below may (launch.cuh)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -317,10 +320,10 @@ int conv_fwd2_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   if (a.stats && grid > a.stats_rows) return UB2_ERR_WORKSPACE;
   const size_t smem = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(Fwd2SmemHeader) + stats_bytes;
   switch (variant) {
-    case 0: note_variant(2); conv_fwd2_kernel<9, false><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
-    case 1: note_variant(2); conv_fwd2_kernel<9, true><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
-    case 2: note_variant(2); conv_fwd2_kernel<1, false><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
-    default: note_variant(2); conv_fwd2_kernel<1, true><<<grid, kF2Threads, smem, stream>>>(tmA0, tmA1, tmB, p); break;
+    case 0: note_variant(2); launch(conv_fwd2_kernel<9, false>, grid, kF2Threads, smem, stream, tmA0, tmA1, tmB, p); break;
+    case 1: note_variant(2); launch(conv_fwd2_kernel<9, true>, grid, kF2Threads, smem, stream, tmA0, tmA1, tmB, p); break;
+    case 2: note_variant(2); launch(conv_fwd2_kernel<1, false>, grid, kF2Threads, smem, stream, tmA0, tmA1, tmB, p); break;
+    default: note_variant(2); launch(conv_fwd2_kernel<1, true>, grid, kF2Threads, smem, stream, tmA0, tmA1, tmB, p); break;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);

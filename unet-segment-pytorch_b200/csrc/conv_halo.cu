@@ -11,6 +11,7 @@
 // the R accumulators, which all live in TMEM (2 x R x N columns, double buffered across items).
 //
 // Warp roles, barriers and epilogue are those of conv_fwd.cu.
+#include "launch.cuh"
 #include <cstdlib>
 #include "conv.h"
 #include "conv_epilogue.cuh"
@@ -41,6 +42,7 @@ template <bool ACC>
 __global__ void __launch_bounds__(kHThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const ConvFwdParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -84,6 +86,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();   // the prologue above touched no global memory; everything below may (launch.cuh)
 
   // item -> (n tile, column segment, row block, image); n tile fastest: neighbours share the A block
   auto decode = [&](int t, int& nt, int& w0, int& h0, int& n) {
@@ -320,8 +323,8 @@ int conv_halo_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   }
   const bool acc = a.stats != nullptr && bn_cols <= 64 && p.n_tiles == 1;
   note_variant(3);
-  if (acc) conv_halo_kernel<true><<<grid, kHThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
-  else conv_halo_kernel<false><<<grid, kHThreads, smem, stream>>>(tmA0, tmA1, tmB, p);
+  if (acc) launch(conv_halo_kernel<true>, grid, kHThreads, smem, stream, tmA0, tmA1, tmB, p);
+  else launch(conv_halo_kernel<false>, grid, kHThreads, smem, stream, tmA0, tmA1, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.grid_used) *a.grid_used = grid;

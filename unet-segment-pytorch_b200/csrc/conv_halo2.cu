@@ -19,6 +19,7 @@
 //   tmem_empty        : in the LEADER, count 2 x epilogue warps (the peer's warps arrive remotely)
 // Work items are paired (2p, 2p+1); an odd tail item gets a phantom partner whose TMA boxes lie
 // outside the tensor (zero fill) and whose epilogue stores nothing.
+#include "launch.cuh"
 #include <cstdlib>
 #include "conv.h"
 #include "conv_epilogue.cuh"
@@ -43,6 +44,7 @@ template <bool ACC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kH2Threads, 1)
 conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const ConvFwdParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -92,6 +94,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   cluster_sync_all();   // barriers of both CTAs are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();   // the prologue above touched no global memory; everything below may (launch.cuh)
 
   // item of this CTA in pair `pr`: (column segment, row block, image); a phantom item (odd tail)
   // gets n = N: every TMA box is out of bounds (zero fill) and nothing is stored
@@ -349,8 +352,8 @@ int conv_halo2_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   const int grid = 2 * clusters;
   if (a.stats && grid > a.stats_rows) return UB2_ERR_WORKSPACE;
   note_variant(4);
-  if (acc) conv_halo2_kernel<true><<<grid, kH2Threads, smem, stream>>>(tmA0, tmA1, tmB, p);
-  else conv_halo2_kernel<false><<<grid, kH2Threads, smem, stream>>>(tmA0, tmA1, tmB, p);
+  if (acc) launch(conv_halo2_kernel<true>, grid, kH2Threads, smem, stream, tmA0, tmA1, tmB, p);
+  else launch(conv_halo2_kernel<false>, grid, kH2Threads, smem, stream, tmA0, tmA1, tmB, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.grid_used) *a.grid_used = grid;

@@ -8,6 +8,7 @@
 // MN-major shared-memory tiles — no transposed copies.  Split-K over pixels: each
 // work item (m tile, n tile, split) writes an fp32 partial tile; a second kernel
 // reduces the splits in a fixed order (deterministic) into the OIHW fp32 gradient.
+#include "launch.cuh"
 #include "conv.h"
 #include "ptx.cuh"
 
@@ -30,6 +31,7 @@ struct WgSmemHeader {
 __global__ void __launch_bounds__(kWThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmDY, const ConvWgradParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -65,6 +67,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();   // the prologue above touched no global memory; everything below may (launch.cuh)
 
   // item -> (split, n tile, m tile); m fastest so CTAs running together share dy tiles in L2.
   // Producer and MMA warps run warp-uniform loops with one elected lane issuing, so operands
@@ -316,7 +319,7 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   note_variant(11);
-  conv_wgrad_kernel<<<grid, kWThreads, smem, stream>>>(tmA0, tmA1, tmDY, p);
+  launch(conv_wgrad_kernel, grid, kWThreads, smem, stream, tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.splits_used) *a.splits_used = splits;

@@ -16,6 +16,7 @@
 // MN-major shared-memory tiles — no transposed copies.  Split-K over pixels: each
 // work item (m tile, n tile, split) writes an fp32 partial tile; a second kernel
 // reduces the splits in a fixed order (deterministic) into the OIHW fp32 gradient.
+#include "launch.cuh"
 #include <cstdlib>
 #include "conv.h"
 #include "ptx.cuh"
@@ -40,6 +41,7 @@ struct Wg2SmemHeader {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kW2Threads, 1)
 conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmDY, const ConvWgradParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -81,6 +83,7 @@ conv_wgrad2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();   // the prologue above touched no global memory; everything below may (launch.cuh)
 
   // item -> (split, n tile, m tile); m fastest so CTAs running together share dy tiles in L2.
   // Producer and MMA warps run warp-uniform loops with one elected lane issuing, so operands
@@ -326,7 +329,7 @@ int conv_wgrad2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   const int grid = 2 * (max_clusters < total_items ? max_clusters : total_items);
   const size_t smem = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(Wg2SmemHeader);
   note_variant(12);
-  conv_wgrad2_kernel<<<grid, kW2Threads, smem, stream>>>(tmA0, tmA1, tmDY, p);
+  launch(conv_wgrad2_kernel, grid, kW2Threads, smem, stream, tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.splits_used) *a.splits_used = splits;

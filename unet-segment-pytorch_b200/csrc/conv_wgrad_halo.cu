@@ -12,6 +12,7 @@
 // through a small ring in 64-pixel pieces and is reused by every tap.  Accumulators (up to five
 // 128 x N tiles) stay in TMEM for the whole pixel range; fp32 partial tiles per split are folded
 // by wgrad_reduce_kernel in a fixed order.
+#include "launch.cuh"
 #include "conv.h"
 #include "ptx.cuh"
 
@@ -41,6 +42,7 @@ __device__ __forceinline__ int tap_off(int t) { return ((t / 3) * kGRW + (t % 3)
 __global__ void __launch_bounds__(kGThreads, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmDY, const WgHaloParams p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -77,6 +79,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();   // the prologue above touched no global memory; everything below may (launch.cuh)
 
   // item -> (channel chunk, tap group, split); the items of one split are neighbours (share dy in L2)
   auto decode_item = [&](int it, int& c, int& t_begin, int& t_end, int& sp) {
@@ -305,7 +308,7 @@ int conv_wgrad_halo_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   note_variant(13);
-  conv_wgrad_halo_kernel<<<grid, kGThreads, smem, stream>>>(tmA0, tmA1, tmDY, p);
+  launch(conv_wgrad_halo_kernel, grid, kGThreads, smem, stream, tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.splits_used) *a.splits_used = splits;

@@ -20,6 +20,7 @@
 // through a small ring in 64-pixel pieces and is reused by every tap.  Accumulators (up to five
 // 128 x N tiles) stay in TMEM for the whole pixel range; fp32 partial tiles per split are folded
 // by wgrad_reduce_kernel in a fixed order.
+#include "launch.cuh"
 #include <cstdlib>
 #include "conv.h"
 #include "ptx.cuh"
@@ -57,6 +58,7 @@ __device__ __forceinline__ int tap_off2(int t) { return ((t / 3) * kG2RW + (t % 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 conv_wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmDY, const WgHalo2Params p) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
@@ -94,6 +96,7 @@ conv_wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_c
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();   // the prologue above touched no global memory; everything below may (launch.cuh)
 
   // pair item -> (two neighbouring channel chunks, tap group, split); this CTA owns chunk 2k + rank
   const int pair_groups = p.tapsplit ? 1 : (p.kchunks / 2) * p.tapgroups;
@@ -353,7 +356,7 @@ int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   const size_t smem = 1024 + 2 * static_cast<size_t>(p.a_bytes) + static_cast<size_t>(b_stages) * p.b_stage_bytes +
                       sizeof(WgHalo2Header);
   note_variant(14);
-  conv_wgrad_halo2_kernel<<<grid, kG2Threads, smem, stream>>>(tmA0, tmA1, tmDY, p);
+  launch(conv_wgrad_halo2_kernel, grid, kG2Threads, smem, stream, tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.splits_used) *a.splits_used = splits;

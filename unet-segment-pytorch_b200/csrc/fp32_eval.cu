@@ -10,6 +10,7 @@
 //   f32_upsample    : bilinear align_corners=True (+ F.pad border)                       (layers.py:78,98-102)
 //   f32_gate        : AttentionGate.forward after the two 1x1 projections                (layers.py:183-192)
 //   f32_outc        : OutConv, NHWC -> NCHW logits                                       (layers.py:120)
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "ptx.cuh"
@@ -20,6 +21,8 @@ namespace ub2 {
 
 __global__ void f32_pack_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin,
                                        int taps) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -36,6 +39,8 @@ __global__ void __launch_bounds__(256)
 f32_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
                    const float* __restrict__ shift, float* __restrict__ out, int N, int Cin, int H, int W,
                    int Cout) {
+  pdl_trigger();
+  pdl_wait();
   const int c4s = Cout / 4;
   const long long total = static_cast<long long>(N) * H * W * c4s;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -71,6 +76,8 @@ f32_conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 
 __global__ void __launch_bounds__(256)
 f32_maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c4s = C / 4, Hp = H / 2, Wp = W / 2;
   const long long total = static_cast<long long>(N) * Hp * Wp * c4s;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -112,6 +119,8 @@ __device__ __forceinline__ float4 lerp4(const float* __restrict__ base, int win,
 __global__ void __launch_bounds__(256)
 f32_upsample_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int hin, int win, int hu,
                     int wu, int Ho, int Wo, int C, float rh, float rw) {
+  pdl_trigger();
+  pdl_wait();
   const int c4s = C / 4;
   const int pt = (Ho - hu) / 2, pl = (Wo - wu) / 2;
   const long long total = static_cast<long long>(N) * Ho * Wo * c4s;
@@ -143,6 +152,8 @@ f32_gate_kernel(const float* __restrict__ q, const float* __restrict__ xp, const
                 const float* __restrict__ hx, const float* __restrict__ wpsi, const float* __restrict__ spsi,
                 const float* __restrict__ hpsi, float* __restrict__ out, int N, int hin, int win, int H, int W,
                 int Ci, int Cx, float rh, float rw) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long pixels = static_cast<long long>(N) * H * W;
   const long long warps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
@@ -183,6 +194,8 @@ f32_gate_kernel(const float* __restrict__ q, const float* __restrict__ xp, const
 __global__ void __launch_bounds__(256)
 f32_outc_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                 float* __restrict__ logits, int N, int H, int W, int C, int K) {
+  pdl_trigger();
+  pdl_wait();
   const long long HW = static_cast<long long>(H) * W;
   const long long pixels = static_cast<long long>(N) * HW;
   for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < pixels;
@@ -220,8 +233,7 @@ extern "C" {
 int ub2_f32_pack_weight(const float* w, float* out, int Cout, int Cin, int taps, void* stream) {
   if (Cout <= 0 || Cin <= 0 || (taps != 1 && taps != 9)) return UB2_ERR_SHAPE;
   const long long total = static_cast<long long>(Cout) * Cin * taps;
-  f32_pack_weight_kernel<<<stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, out, Cout, Cin, taps);
+  launch(f32_pack_weight_kernel, stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream), w, out, Cout, Cin, taps);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -229,16 +241,14 @@ int ub2_f32_conv_in(const float* x, const float* w, const float* scale, const fl
                     int Cin, int H, int W, int Cout, void* stream) {
   if (Cout % 4 != 0 || Cin <= 0 || N <= 0) return UB2_ERR_SHAPE;
   const long long total = static_cast<long long>(N) * H * W * (Cout / 4);
-  f32_conv_in_kernel<<<stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, w, scale, shift, out, N, Cin, H, W, Cout);
+  launch(f32_conv_in_kernel, stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream), x, w, scale, shift, out, N, Cin, H, W, Cout);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_f32_maxpool(const float* in, float* out, int N, int H, int W, int C, void* stream) {
   if (C % 4 != 0 || H < 2 || W < 2 || N <= 0) return UB2_ERR_SHAPE;
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 4);
-  f32_maxpool_kernel<<<stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, out, N, H, W, C);
+  launch(f32_maxpool_kernel, stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream), in, out, N, H, W, C);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -246,8 +256,7 @@ int ub2_f32_upsample(const float* in, float* out, int N, int hin, int win, int h
                      void* stream) {
   if (C % 4 != 0 || Ho < hu || Wo < wu || N <= 0) return UB2_ERR_SHAPE;
   const long long total = static_cast<long long>(N) * Ho * Wo * (C / 4);
-  f32_upsample_kernel<<<stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, out, N, hin, win, hu, wu, Ho, Wo, C, ratio(hin, hu), ratio(win, wu));
+  launch(f32_upsample_kernel, stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream), in, out, N, hin, win, hu, wu, Ho, Wo, C, ratio(hin, hu), ratio(win, wu));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -257,9 +266,7 @@ int ub2_f32_gate(const float* q, const float* xp, const float* x, const float* s
                  void* stream) {
   if (Ci % 4 != 0 || Cx % 4 != 0 || N <= 0) return UB2_ERR_SHAPE;
   const long long pixels = static_cast<long long>(N) * H * W;
-  f32_gate_kernel<<<stream_grid(pixels, 8, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      q, xp, x, scale_g, shift_g, scale_x, shift_x, w_psi, scale_psi, shift_psi, out, N, hin, win, H, W, Ci, Cx,
-      ratio(hin, H), ratio(win, W));
+  launch(f32_gate_kernel, stream_grid(pixels, 8, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream), q, xp, x, scale_g, shift_g, scale_x, shift_x, w_psi, scale_psi, shift_psi, out, N, hin, win, H, W, Ci, Cx, ratio(hin, H), ratio(win, W));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -267,8 +274,7 @@ int ub2_f32_outc(const float* a, const float* w, const float* bias, float* logit
                  int K, void* stream) {
   if (C % 4 != 0 || K <= 0 || K > 8 || N <= 0) return UB2_ERR_SHAPE;
   const long long pixels = static_cast<long long>(N) * H * W;
-  f32_outc_kernel<<<stream_grid(pixels, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      a, w, bias, logits, N, H, W, C, K);
+  launch(f32_outc_kernel, stream_grid(pixels, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream), a, w, bias, logits, N, H, W, C, K);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -14,6 +14,7 @@
 // 8-channel vectors; per-pixel channel reductions are shuffle reductions inside that group,
 // per-channel pixel reductions stay in registers (a thread's channels are fixed) and are
 // combined per block in shared memory, then across blocks by a finalize kernel in double.
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "resample.cuh"
@@ -200,6 +201,8 @@ __device__ __forceinline__ F8 qroll_get(const QRoll<G>& r, int gi) {
 template <int G>
 __global__ void __launch_bounds__(kGateThreads)
 gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* partials, GateGeom g) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float smem[kGateThreads * 8];
   float acc[G][2][8];
 #pragma unroll
@@ -254,6 +257,8 @@ gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat
                 const float* __restrict__ sx, const float* __restrict__ hx,
                 const float* __restrict__ wpsi, float* __restrict__ psi_raw, double* partials,
                 GateGeom g) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float smem[kGateThreads / 32];
   float st[2] = {0.f, 0.f};
   const GateVec v0 = gate_vec(sg, hg, sx, hx, wpsi, threadIdx.x % g.tpp, g.cgs);
@@ -289,6 +294,8 @@ gate_apply_kernel(const float* __restrict__ psi_raw, const float* __restrict__ s
                   const float* __restrict__ hpsi, const __nv_bfloat16* __restrict__ x, int ld_x,
                   __nv_bfloat16* __restrict__ out, int ld_out, float* __restrict__ a_out,
                   int pixels, int cgs) {
+  pdl_trigger();
+  pdl_wait();
   const float s = __ldg(spsi), h = __ldg(hpsi);
   const int total = pixels * cgs;
   const int stride = static_cast<int>(gridDim.x) * blockDim.x;
@@ -333,6 +340,8 @@ gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_
                   int ld_x, const float* __restrict__ a, const float* __restrict__ psi_raw,
                   __nv_bfloat16* __restrict__ dx, int ld_dx, float* __restrict__ dpsin,
                   double* partials, GateGeom g) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float smem[kGateThreads / 32];
   float st[2] = {0.f, 0.f};  // sum dn, sum dn*psi_raw (bn_bwd_finalize convention)
   GATE_PIXEL_LOOP(g) {
@@ -374,6 +383,8 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
                   const float* __restrict__ hg, const float* __restrict__ sx,
                   const float* __restrict__ hx, const float* __restrict__ wpsi,
                   __nv_bfloat16* __restrict__ ds, int ld_ds, double* partials, GateGeom g) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float smem[kGateThreads * 8];
   const float cA = __ldg(coef_psi), cB = __ldg(coef_psi + 1), cC = __ldg(coef_psi + 2);
   const GateVec v0 = gate_vec(sg, hg, sx, hx, wpsi, threadIdx.x % g.tpp, g.cgs);
@@ -426,6 +437,8 @@ __global__ void gate_bwd_finalize_kernel(const double* __restrict__ partials, in
                                          const float* __restrict__ invstd_g, int frozen, float* dgamma_x,
                                          float* dbeta_x, float* dgamma_g, float* dbeta_g, float* dwpsi,
                                          float* coef) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double smem[4 * 128 * 9];
   const int c = blockIdx.x * 8 + threadIdx.x;
   double s[4];
@@ -458,6 +471,8 @@ gate_bwd_xg_kernel(const __nv_bfloat16* __restrict__ ds, int ld_ds, const __nv_b
                    int ld_xp, const __nv_bfloat16* __restrict__ q, int ld_q,
                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ dxp, int ld_dxp,
                    __nv_bfloat16* __restrict__ dgup, int ld_dg, GateGeom g) {
+  pdl_trigger();
+  pdl_wait();
   F8 cf[6];
   {
     const int cg0 = threadIdx.x % g.tpp;
@@ -525,9 +540,9 @@ int ub2_gate_upstats(const void* q, int ld_q, int N, int hin, int win, int H, in
   const int grid = gate_strip_grid(g);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   if (g.cgs > g.tpp)
-    gate_upstats_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<cbf>(q), ld_q, partials, g);
+    launch(gate_upstats_kernel<2>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(q), ld_q, partials, g);
   else
-    gate_upstats_kernel<1><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<cbf>(q), ld_q, partials, g);
+    launch(gate_upstats_kernel<1>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(q), ld_q, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -541,13 +556,9 @@ int ub2_gate_psi(const void* q, int ld_q, const void* xp, int ld_xp, const float
   const int grid = gate_strip_grid(g);
   if (partials != nullptr && grid != rows) return UB2_ERR_WORKSPACE;
   if (g.cgs > g.tpp)
-    gate_psi_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi,
-        psi_raw, partials, g);
+    launch(gate_psi_kernel<2>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi, psi_raw, partials, g);
   else
-    gate_psi_kernel<1><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi,
-        psi_raw, partials, g);
+    launch(gate_psi_kernel<1>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi, psi_raw, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -556,10 +567,7 @@ int ub2_gate_apply(const float* psi_raw, const float* scale_psi, const float* sh
                    void* stream) {
   if (Cx % 8 != 0 || N <= 0 || static_cast<double>(N) * H * W * (Cx / 8) >= 2.0e9) return UB2_ERR_SHAPE;
   const int pixels = static_cast<int>(N) * H * W;
-  gate_apply_kernel<<<stream_grid(pixels * (Cx / 8), 256, num_sms()), 256, 0,
-                      static_cast<cudaStream_t>(stream)>>>(
-      psi_raw, scale_psi, shift_psi, static_cast<cbf>(x), ld_x, static_cast<bf>(out), ld_out, a_out,
-      pixels, Cx / 8);
+  launch(gate_apply_kernel, stream_grid(pixels * (Cx / 8), 256, num_sms()), 256, 0, static_cast<cudaStream_t>(stream), psi_raw, scale_psi, shift_psi, static_cast<cbf>(x), ld_x, static_cast<bf>(out), ld_out, a_out, pixels, Cx / 8);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -572,13 +580,9 @@ int ub2_gate_bwd_a(const void* dout, int ld_do, const void* x, int ld_x, const f
   const int grid = gate_grid(g, 8);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   if (g.cgs > g.tpp)
-    gate_bwd_a_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, static_cast<bf>(dx), ld_dx,
-        dpsin, partials, g);
+    launch(gate_bwd_a_kernel<2>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, static_cast<bf>(dx), ld_dx, dpsin, partials, g);
   else
-    gate_bwd_a_kernel<1><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, static_cast<bf>(dx), ld_dx,
-        dpsin, partials, g);
+    launch(gate_bwd_a_kernel<1>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(dout), ld_do, static_cast<cbf>(x), ld_x, a, psi_raw, static_cast<bf>(dx), ld_dx, dpsin, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -593,13 +597,9 @@ int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_p
   const int grid = gate_strip_grid(g);
   if (grid != rows) return UB2_ERR_WORKSPACE;
   if (g.cgs > g.tpp)
-    gate_bwd_s_kernel<2><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g,
-        scale_x, shift_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
+    launch(gate_bwd_s_kernel<2>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
   else
-    gate_bwd_s_kernel<1><<<grid, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g,
-        scale_x, shift_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
+    launch(gate_bwd_s_kernel<1>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -609,9 +609,7 @@ int ub2_gate_bwd_finalize(const double* partials, int rows, int Ci, double count
                           float* dbeta_x, float* dgamma_g, float* dbeta_g, float* dwpsi, float* coef,
                           void* stream) {
   if (Ci <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  gate_bwd_finalize_kernel<<<(Ci + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream)>>>(
-      partials, rows, Ci, count, gamma_x, mean_x, invstd_x, gamma_g, mean_g, invstd_g, frozen, dgamma_x,
-      dbeta_x, dgamma_g, dbeta_g, dwpsi, coef);
+  launch(gate_bwd_finalize_kernel, (Ci + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream), partials, rows, Ci, count, gamma_x, mean_x, invstd_x, gamma_g, mean_g, invstd_g, frozen, dgamma_x, dbeta_x, dgamma_g, dbeta_g, dwpsi, coef);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -624,13 +622,9 @@ int ub2_gate_bwd_xg(const void* ds, int ld_ds, const void* xp, int ld_xp, const 
   const int grid = gate_strip_grid(g);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (g.cgs > g.tpp)
-    gate_bwd_xg_kernel<2><<<grid, kGateThreads, 0, s>>>(static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp,
-                                                        static_cast<cbf>(q), ld_q, coef, static_cast<bf>(dxp),
-                                                        ld_dxp, static_cast<bf>(dgup), ld_dg, g);
+    launch(gate_bwd_xg_kernel<2>, grid, kGateThreads, 0, s, static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp, static_cast<cbf>(q), ld_q, coef, static_cast<bf>(dxp), ld_dxp, static_cast<bf>(dgup), ld_dg, g);
   else
-    gate_bwd_xg_kernel<1><<<grid, kGateThreads, 0, s>>>(static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp,
-                                                        static_cast<cbf>(q), ld_q, coef, static_cast<bf>(dxp),
-                                                        ld_dxp, static_cast<bf>(dgup), ld_dg, g);
+    launch(gate_bwd_xg_kernel<1>, grid, kGateThreads, 0, s, static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp, static_cast<cbf>(q), ld_q, coef, static_cast<bf>(dxp), ld_dxp, static_cast<bf>(dgup), ld_dg, g);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -6,6 +6,7 @@
 //    and its weight gradient (no data gradient: the input needs none).
 //  * outc: OutConv's 1x1 conv with bias (layers.py:120) C -> n_classes, writing fp32 NCHW
 //    logits, and its backward (data gradient NHWC bf16, weight / bias gradients).
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "vec.cuh"
@@ -23,6 +24,8 @@ template <bool REGW>
 __global__ void __launch_bounds__(kHeadThreads)
 conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
                    int ld_y, double* partials, int N, int Cin, int H, int W, int Cout) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_dyn[];
   float* s_w = s_dyn;                         // [Cin*9][Cout]
   float* s_red = s_dyn + Cin * 9 * Cout;      // [lanes][cgs][16]
@@ -106,6 +109,8 @@ conv_in_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __n
 __global__ void __launch_bounds__(kHeadThreads)
 conv_in_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
                     int ld_y, double* partials, int N, int H, int W, int Cout) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_red[];  // [lanes][cgs][16]
   const int cgs = Cout / 8;
   const int lanes = blockDim.x / cgs;
@@ -182,6 +187,8 @@ conv_in_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ w, __
 __global__ void __launch_bounds__(kHeadThreads)
 conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int ld_dy,
                      double* partials, int N, int Cin, int H, int W, int Cout) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_red[];  // [lanes][cgs][8]
   const int ci = blockIdx.y;
   const int cgs = Cout / 8;
@@ -235,6 +242,8 @@ conv_in_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restric
 __global__ void __launch_bounds__(kHeadThreads, 2)
 conv_in_wgrad4_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int ld_dy,
                       double* partials, int N, int H, int W, int Cout) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_red[];  // [lanes][cgs][8]
   const int cgs = Cout / 8;
   const int lanes = blockDim.x / cgs;
@@ -308,6 +317,8 @@ conv_in_wgrad4_kernel(const float* __restrict__ x, const __nv_bfloat16* __restri
 // grad[co][ci][t] += sum_rows partials[row][ci][t][co];  blockDim = (32, 32)
 __global__ void conv_in_wgrad_finalize_kernel(const double* __restrict__ partials, int rows, int Cin,
                                               int Cout, float* grad) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double smem[32 * 33];
   const int total = Cout * Cin * 9;
   const int i = blockIdx.x * 32 + threadIdx.x;  // index into the [ci][t][co] row layout
@@ -330,6 +341,8 @@ template <int KMAX>
 __global__ void __launch_bounds__(kHeadThreads)
 outc_fwd_kernel(const __nv_bfloat16* __restrict__ a, int ld_a, const float* __restrict__ w,
                 const float* __restrict__ bias, float* __restrict__ logits, HeadGeom g) {
+  pdl_trigger();
+  pdl_wait();
   const int slot = threadIdx.x / g.tpp, j = threadIdx.x % g.tpp;
   const bool single = g.cgs <= g.tpp;
   F8 wreg[KMAX];
@@ -395,6 +408,8 @@ __global__ void __launch_bounds__(kHeadThreads)
 outc_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ a, int ld_a,
                 const float* __restrict__ w, __nv_bfloat16* __restrict__ da, int ld_da,
                 double* partials, HeadGeom g) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_red[];  // [256][8]
   const int slot = threadIdx.x / g.tpp, j = threadIdx.x % g.tpp;
   // G channel groups per thread (C <= 256*G), KMAX >= n_classes
@@ -514,6 +529,8 @@ outc_bwd_kernel(const float* __restrict__ dl, const __nv_bfloat16* __restrict__ 
 // blockDim = (32, 32)
 __global__ void outc_bwd_finalize_kernel(const double* __restrict__ partials, int rows, int K, int C,
                                          float* dw, float* db) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double smem[32 * 33];
   const int total = K * C + K;
   const int i = blockIdx.x * 32 + threadIdx.x;
@@ -563,15 +580,11 @@ int ub2_conv_in_fwd(const float* x, const float* w, void* y, int ld_y, double* p
   if (partials != nullptr && grid != rows) return UB2_ERR_WORKSPACE;
   const size_t smem = (static_cast<size_t>(Cin) * 9 * Cout + static_cast<size_t>(lanes) * cgs * 16) * sizeof(float);
   if (Cin == 1 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
-    conv_in_fwd4_kernel<<<grid, block, static_cast<size_t>(lanes) * cgs * 16 * sizeof(float),
-                          static_cast<cudaStream_t>(stream)>>>(x, w, static_cast<__nv_bfloat16*>(y), ld_y,
-                                                               partials, N, H, W, Cout);
+    launch(conv_in_fwd4_kernel, grid, block, static_cast<size_t>(lanes) * cgs * 16 * sizeof(float), static_cast<cudaStream_t>(stream), x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, H, W, Cout);
   else if (Cin == 1)
-    conv_in_fwd_kernel<true><<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
-        x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, Cin, H, W, Cout);
+    launch(conv_in_fwd_kernel<true>, grid, block, smem, static_cast<cudaStream_t>(stream), x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, Cin, H, W, Cout);
   else
-    conv_in_fwd_kernel<false><<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
-        x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, Cin, H, W, Cout);
+    launch(conv_in_fwd_kernel<false>, grid, block, smem, static_cast<cudaStream_t>(stream), x, w, static_cast<__nv_bfloat16*>(y), ld_y, partials, N, Cin, H, W, Cout);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -588,13 +601,11 @@ int ub2_conv_in_wgrad(const float* x, const void* dy, int ld_dy, double* partial
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (Cin == 1 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       static_cast<double>(N) * H * W < 4.0e9)
-    conv_in_wgrad4_kernel<<<grid, block, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dy), ld_dy, partials, N,
-                                                    H, W, Cout);
+    launch(conv_in_wgrad4_kernel, grid, block, smem, s, x, static_cast<const __nv_bfloat16*>(dy), ld_dy, partials, N, H, W, Cout);
   else
-    conv_in_wgrad_kernel<<<dim3(grid, Cin), block, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dy),
-                                                             ld_dy, partials, N, Cin, H, W, Cout);
+    launch(conv_in_wgrad_kernel, dim3(grid, Cin), block, smem, s, x, static_cast<const __nv_bfloat16*>(dy), ld_dy, partials, N, Cin, H, W, Cout);
   const int total = Cout * Cin * 9;
-  conv_in_wgrad_finalize_kernel<<<(total + 31) / 32, dim3(32, 32), 0, s>>>(partials, grid, Cin, Cout, grad);
+  launch(conv_in_wgrad_finalize_kernel, (total + 31) / 32, dim3(32, 32), 0, s, partials, grid, Cin, Cout, grad);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -613,9 +624,9 @@ int ub2_outc_fwd(const void* a, int ld_a, const float* w, const float* bias, flo
   const int grid = stream_grid((g.pixels + 3) / 4, g.slots, num_sms(), 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* ap = static_cast<const __nv_bfloat16*>(a);
-  if (K <= 2) outc_fwd_kernel<2><<<grid, kHeadThreads, 0, s>>>(ap, ld_a, w, bias, logits, g);
-  else if (K <= 4) outc_fwd_kernel<4><<<grid, kHeadThreads, 0, s>>>(ap, ld_a, w, bias, logits, g);
-  else outc_fwd_kernel<8><<<grid, kHeadThreads, 0, s>>>(ap, ld_a, w, bias, logits, g);
+  if (K <= 2) launch(outc_fwd_kernel<2>, grid, kHeadThreads, 0, s, ap, ld_a, w, bias, logits, g);
+  else if (K <= 4) launch(outc_fwd_kernel<4>, grid, kHeadThreads, 0, s, ap, ld_a, w, bias, logits, g);
+  else launch(outc_fwd_kernel<8>, grid, kHeadThreads, 0, s, ap, ld_a, w, bias, logits, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -635,15 +646,15 @@ int ub2_outc_bwd(const float* dlogits, const void* a, int ld_a, const float* w, 
   const bool two = g.cgs > g.tpp;
 #define UB2_OUTC_BWD(KM)                                                                              \
   do {                                                                                                \
-    if (two) outc_bwd_kernel<KM, 2><<<grid, kHeadThreads, smem, s>>>(dlogits, ap, ld_a, w, dap, ld_da, partials, g); \
-    else outc_bwd_kernel<KM, 1><<<grid, kHeadThreads, smem, s>>>(dlogits, ap, ld_a, w, dap, ld_da, partials, g);    \
+    if (two) launch(outc_bwd_kernel<KM, 2>, grid, kHeadThreads, smem, s, dlogits, ap, ld_a, w, dap, ld_da, partials, g); \
+    else launch(outc_bwd_kernel<KM, 1>, grid, kHeadThreads, smem, s, dlogits, ap, ld_a, w, dap, ld_da, partials, g);    \
   } while (0)
   if (K <= 2) UB2_OUTC_BWD(2);
   else if (K <= 4) UB2_OUTC_BWD(4);
   else UB2_OUTC_BWD(8);
 #undef UB2_OUTC_BWD
   const int total = K * C + K;
-  outc_bwd_finalize_kernel<<<(total + 31) / 32, dim3(32, 32), 0, s>>>(partials, grid, K, C, dw, db);
+  launch(outc_bwd_finalize_kernel, (total + 31) / 32, dim3(32, 32), 0, s, partials, grid, K, C, dw, db);
   return static_cast<int>(cudaGetLastError());
 }
 

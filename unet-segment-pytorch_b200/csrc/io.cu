@@ -20,6 +20,7 @@
 //
 // Output side (scripts/predict.py:138-166, 232-240): mask = (softmax(logits)[1] > thr) * 255 as
 // uint8 and tumor_ratio = #(mask > 127) / pixels, per image, without the logits leaving the GPU.
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "ptx.cuh"
@@ -43,6 +44,8 @@ __global__ void __launch_bounds__(kIoThreads)
 prepare_batch_kernel(const unsigned char* __restrict__ img, const unsigned char* __restrict__ label,
                      const unsigned char* __restrict__ flags, int N, int H, int W, float mean, float stdv,
                      float* __restrict__ x, long long* __restrict__ t) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_lut[256];
   s_lut[threadIdx.x] = normalised_level(threadIdx.x, mean, stdv);
   __syncthreads();
@@ -97,6 +100,8 @@ __global__ void __launch_bounds__(kIoThreads)
 prepare_batch_scalar_kernel(const unsigned char* __restrict__ img, const unsigned char* __restrict__ label,
                             const unsigned char* __restrict__ flags, int N, int H, int W, float mean,
                             float stdv, float* __restrict__ x, long long* __restrict__ t) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_lut[256];
   s_lut[threadIdx.x] = normalised_level(threadIdx.x, mean, stdv);
   __syncthreads();
@@ -128,6 +133,8 @@ __device__ __forceinline__ float tumour_probability(float z0, float z1) {
 __global__ void __launch_bounds__(kIoThreads)
 predict_mask_kernel(const float* __restrict__ logits, long long HW, int chunks_per_image, float threshold,
                     unsigned char* __restrict__ mask, int* __restrict__ positives) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int s_warp[kIoThreads / 32];
   const int n = blockIdx.x / chunks_per_image, chunk = blockIdx.x % chunks_per_image;
   const float* z0 = logits + static_cast<long long>(n) * 2 * HW;
@@ -188,12 +195,10 @@ int ub2_prepare_batch(const unsigned char* images, const unsigned char* labels, 
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(targets) & 31) == 0;
   if (vec) {
     const long long items = (static_cast<long long>(N) * H * (W / 4) + 3) / 4;   // 4 items per thread
-    prepare_batch_kernel<<<stream_grid(items, kIoThreads, num_sms(), 8), kIoThreads, 0, s>>>(
-        images, labels, flags, N, H, W, mean, std, x, targets);
+    launch(prepare_batch_kernel, stream_grid(items, kIoThreads, num_sms(), 8), kIoThreads, 0, s, images, labels, flags, N, H, W, mean, std, x, targets);
   } else {
     const long long items = static_cast<long long>(N) * H * W;
-    prepare_batch_scalar_kernel<<<stream_grid(items, kIoThreads, num_sms(), 8), kIoThreads, 0, s>>>(
-        images, labels, flags, N, H, W, mean, std, x, targets);
+    launch(prepare_batch_scalar_kernel, stream_grid(items, kIoThreads, num_sms(), 8), kIoThreads, 0, s, images, labels, flags, N, H, W, mean, std, x, targets);
   }
   return static_cast<int>(cudaGetLastError());
 }
@@ -211,8 +216,7 @@ int ub2_predict_mask(const float* logits, int N, int C, long long HW, float thre
   const long long max_chunks = (HW + 4095) / 4096;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
-  predict_mask_kernel<<<static_cast<unsigned>(N * chunks), kIoThreads, 0, s>>>(logits, HW, static_cast<int>(chunks),
-                                                                               threshold, mask, positives);
+  launch(predict_mask_kernel, static_cast<unsigned>(N * chunks), kIoThreads, 0, s, logits, HW, static_cast<int>(chunks), threshold, mask, positives);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -11,6 +11,7 @@
 // loss stays on the host side of the ABI.  seg_stats_bwd is the second pass:
 //   dz[i,k] = dce[n,t_i] (p_ik - y_ik) + p_ik (g_ik - sum_c g_ic p_ic),
 //   g_ic = dI[n,c] [t_i = c] + dP[n,c]
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "vec.cuh"
@@ -46,6 +47,8 @@ template <int C>
 __global__ void __launch_bounds__(kLossThreads)
 seg_stats_kernel(const float* __restrict__ logits, const long long* __restrict__ targets, long long HW,
                  double* partials) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_red[kLossThreads / 32][C * 4];
   const int n = blockIdx.y;
   const float* z = logits + static_cast<size_t>(n) * C * HW;
@@ -88,6 +91,8 @@ seg_stats_kernel(const float* __restrict__ logits, const long long* __restrict__
 // stats[n][k][c] (k = cnt, ce, I, P) as fp32;  grid = (ceil(C*4/32), N), blockDim = (32, 32)
 __global__ void seg_stats_finalize_kernel(const double* __restrict__ partials, int blocks, int N, int C,
                                           float* stats) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double smem[32 * 33];
   const int n = blockIdx.y;
   const int r = blockIdx.x * 32 + threadIdx.x;
@@ -108,6 +113,8 @@ __global__ void __launch_bounds__(256)
 dice_bce_head_kernel(const float* __restrict__ stats, int N, int C, float ce_weight, float dice_weight,
                      float class_weight, float ce_smooth, float dice_smooth, int ignore_background,
                      float* __restrict__ loss, float* __restrict__ coef) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double s_bce[256], s_dice[256];
   const int c0 = (ignore_background && C > 1) ? 1 : 0;
   const float inv_n = 1.f / static_cast<float>(N);
@@ -152,6 +159,8 @@ __global__ void __launch_bounds__(kLossThreads)
 seg_stats_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ targets,
                      const float* __restrict__ coef, const float* __restrict__ gscale, long long HW,
                      float* __restrict__ dlogits) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y;
   const float* z = logits + static_cast<size_t>(n) * C * HW;
   const long long* t = targets + static_cast<size_t>(n) * HW;
@@ -189,14 +198,14 @@ seg_stats_bwd_kernel(const float* __restrict__ logits, const long long* __restri
 template <int C>
 static int launch_stats(const float* logits, const long long* targets, int N, long long HW,
                         double* partials, int blocks, float* stats, cudaStream_t s) {
-  seg_stats_kernel<C><<<dim3(blocks, N), kLossThreads, 0, s>>>(logits, targets, HW, partials);
-  seg_stats_finalize_kernel<<<dim3((C * 4 + 31) / 32, N), dim3(32, 32), 0, s>>>(partials, blocks, N, C, stats);
+  launch(seg_stats_kernel<C>, dim3(blocks, N), kLossThreads, 0, s, logits, targets, HW, partials);
+  launch(seg_stats_finalize_kernel, dim3((C * 4 + 31) / 32, N), dim3(32, 32), 0, s, partials, blocks, N, C, stats);
   return static_cast<int>(cudaGetLastError());
 }
 template <int C>
 static int launch_bwd(const float* logits, const long long* targets, const float* coef, const float* gscale,
                       int N, long long HW, float* dlogits, int blocks, cudaStream_t s) {
-  seg_stats_bwd_kernel<C><<<dim3(blocks, N), kLossThreads, 0, s>>>(logits, targets, coef, gscale, HW, dlogits);
+  launch(seg_stats_bwd_kernel<C>, dim3(blocks, N), kLossThreads, 0, s, logits, targets, coef, gscale, HW, dlogits);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -239,8 +248,7 @@ int ub2_dice_bce_head(const float* stats, int N, int C, float ce_weight, float d
                       float ce_smooth, float dice_smooth, int ignore_background, float* loss, float* coef,
                       void* stream) {
   if (N <= 0 || C < 1 || C > kLossMaxC) return UB2_ERR_SHAPE;
-  dice_bce_head_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, N, C, ce_weight, dice_weight, class_weight, ce_smooth, dice_smooth, ignore_background, loss, coef);
+  launch(dice_bce_head_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), stats, N, C, ce_weight, dice_weight, class_weight, ce_smooth, dice_smooth, ignore_background, loss, coef);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -7,6 +7,7 @@
 // (metrics.py:160-227), which count such pixels on the prediction side, can be derived from
 // the same matrix.  Integer arithmetic: results are bit-exact and order independent.
 // argmax follows torch: the first maximum wins (strict >).
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "vec.cuh"
@@ -24,6 +25,8 @@ __global__ void __launch_bounds__(kCmThreads)
 confusion_kernel(const void* __restrict__ pred, const long long* __restrict__ target, int N, int C,
                  long long HW, long long ignore_index, int has_ignore, float threshold,
                  unsigned long long* cm, unsigned char* mask_out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ unsigned int s_cm[(kCmMaxC + 1) * (kCmMaxC + 1)];
   const int B = C + 1;
   for (int i = threadIdx.x; i < B * B; i += blockDim.x) s_cm[i] = 0u;
@@ -89,14 +92,11 @@ int ub2_confusion(const void* pred, const long long* target, int mode, int N, in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   unsigned long long* out = reinterpret_cast<unsigned long long*>(cm);
   if (mode == 0)
-    confusion_kernel<0><<<grid, kCmThreads, 0, s>>>(pred, target, N, C, HW, ignore_index, has_ignore,
-                                                    threshold, out, mask_out);
+    launch(confusion_kernel<0>, grid, kCmThreads, 0, s, pred, target, N, C, HW, ignore_index, has_ignore, threshold, out, mask_out);
   else if (mode == 1)
-    confusion_kernel<1><<<grid, kCmThreads, 0, s>>>(pred, target, N, C, HW, ignore_index, has_ignore,
-                                                    threshold, out, mask_out);
+    launch(confusion_kernel<1>, grid, kCmThreads, 0, s, pred, target, N, C, HW, ignore_index, has_ignore, threshold, out, mask_out);
   else
-    confusion_kernel<2><<<grid, kCmThreads, 0, s>>>(pred, target, N, C, HW, ignore_index, has_ignore,
-                                                    threshold, out, mask_out);
+    launch(confusion_kernel<2>, grid, kCmThreads, 0, s, pred, target, N, C, HW, ignore_index, has_ignore, threshold, out, mask_out);
   return static_cast<int>(cudaGetLastError());
 }
 

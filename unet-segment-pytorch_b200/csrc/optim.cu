@@ -9,6 +9,7 @@
 //
 // Everything the host would have to know per step (step count, learning rate) lives in device
 // memory, so the step can sit inside a captured CUDA graph while a scheduler changes the rate.
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "vec.cuh"
@@ -39,6 +40,8 @@ __global__ void __launch_bounds__(kOptThreads)
 grad_sumsq_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ numel,
                   const int2* __restrict__ chunks, int chunk_elems, int T, double* __restrict__ partial,
                   float* __restrict__ step) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double s_red[kOptThreads / 32];
   const int2 ch = chunks[blockIdx.x];
   const float* g = reinterpret_cast<const float*>(ptrs[1 * T + ch.x]);
@@ -83,6 +86,8 @@ adamw_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ n
              const int* __restrict__ group, const int2* __restrict__ chunks, int nchunks, int chunk_elems,
              int T, const double* __restrict__ partial, const float* __restrict__ hyper,
              const float* __restrict__ step, float* __restrict__ total_norm, int write_grads) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double s_red[kOptThreads / 32];
   double acc = 0.0;
   for (int i = threadIdx.x; i < nchunks; i += kOptThreads) acc += partial[i];
@@ -155,6 +160,8 @@ adamw_kernel(const long long* __restrict__ ptrs, const long long* __restrict__ n
 __global__ void __launch_bounds__(kOptThreads)
 ema_update_kernel(const long long* __restrict__ desc, const int2* __restrict__ chunks, int chunk_elems,
                   const float* __restrict__ decay_ptr) {
+  pdl_trigger();
+  pdl_wait();
   const int2 ch = chunks[blockIdx.x];
   const long long* d = desc + 4 * ch.x;
   const long long n = d[2];
@@ -203,8 +210,7 @@ int ub2_adamw_chunk_elems(void) { return 16384; }
 int ub2_grad_sumsq(const long long* ptrs, const long long* numel, const int* chunks, int nchunks, int T,
                    double* partial, float* step, void* stream) {
   if (nchunks <= 0 || T <= 0) return UB2_ERR_SHAPE;
-  grad_sumsq_kernel<<<nchunks, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      ptrs, numel, reinterpret_cast<const int2*>(chunks), ub2_adamw_chunk_elems(), T, partial, step);
+  launch(grad_sumsq_kernel, nchunks, kOptThreads, 0, static_cast<cudaStream_t>(stream), ptrs, numel, reinterpret_cast<const int2*>(chunks), ub2_adamw_chunk_elems(), T, partial, step);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -212,16 +218,13 @@ int ub2_adamw_step(const long long* ptrs, const long long* numel, const int* gro
                    int nchunks, int T, const double* partial, const float* hyper, const float* step,
                    float* total_norm, int write_grads, void* stream) {
   if (nchunks <= 0 || T <= 0) return UB2_ERR_SHAPE;
-  adamw_kernel<<<nchunks, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      ptrs, numel, group, reinterpret_cast<const int2*>(chunks), nchunks, ub2_adamw_chunk_elems(), T, partial,
-      hyper, step, total_norm, write_grads);
+  launch(adamw_kernel, nchunks, kOptThreads, 0, static_cast<cudaStream_t>(stream), ptrs, numel, group, reinterpret_cast<const int2*>(chunks), nchunks, ub2_adamw_chunk_elems(), T, partial, hyper, step, total_norm, write_grads);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_ema_update(const long long* desc, const int* chunks, int nchunks, const float* decay, void* stream) {
   if (nchunks <= 0) return UB2_ERR_SHAPE;
-  ema_update_kernel<<<nchunks, kOptThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      desc, reinterpret_cast<const int2*>(chunks), ub2_adamw_chunk_elems(), decay);
+  launch(ema_update_kernel, nchunks, kOptThreads, 0, static_cast<cudaStream_t>(stream), desc, reinterpret_cast<const int2*>(chunks), ub2_adamw_chunk_elems(), decay);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -4,6 +4,7 @@
 //   fwd pack   (Cout, taps, Cin)         : K-major B operand of the forward implicit GEMM
 //   dgrad pack (Cin, taps flipped, Cout) : the same kernel computes the data gradient
 // and the split-K partial weight gradients are folded back into the OIHW fp32 .grad.
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "vec.cuh"
@@ -108,6 +109,8 @@ __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
                    __nv_bfloat16* __restrict__ dgrad, int Cout, int Cin,
                    const float* __restrict__ out_scale) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __nv_bfloat16 tile[kPackT][kPackT * 9 + 2];
   pack_tile<TAPS, FULL>(w, fwd, dgrad, Cout, Cin, out_scale, blockIdx.x, blockIdx.y, tile);
 }
@@ -116,6 +119,8 @@ pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ fwd,
 // desc[t] = {w, fwd, dgrad, Cout, Cin, taps} as int64, blocks[b] = {tensor, ci tile, co tile, -}.
 __global__ void __launch_bounds__(256)
 pack_weights_multi_kernel(const long long* __restrict__ desc, const int4* __restrict__ blocks) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __nv_bfloat16 tile[kPackT][kPackT * 9 + 2];
   const int4 b = blocks[blockIdx.x];
   const long long* d = desc + 6 * b.x;
@@ -132,6 +137,8 @@ pack_weights_multi_kernel(const long long* __restrict__ desc, const int4* __rest
 // element of slot 0 is read (by lane 0) before the block-wide barrier and written after it.
 __global__ void __launch_bounds__(256)
 wgrad_presum_kernel(float* __restrict__ partial, int splits, long long quads) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 s_red[8][32];
   const long long q = static_cast<long long>(blockIdx.x) * 32 + threadIdx.x;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -198,6 +205,8 @@ template <int TAPS>
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin,
                     float* __restrict__ grad, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][kRedCi * 9 + 1];
   reduce_tile<TAPS>(partial, splits, Cout, Cin, grad, accumulate, blockIdx.x, blockIdx.y, tile);
 }
@@ -218,6 +227,8 @@ __device__ __forceinline__ int find_item(const ReduceItems& t, int block) {
 
 __global__ void __launch_bounds__(256)
 wgrad_presum_multi_kernel(const __grid_constant__ ReduceItems t) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 s_red[8][32];
   const int i = find_item(t, blockIdx.x);
   const Ub2ReduceItem& it = t.item[i];
@@ -247,6 +258,8 @@ wgrad_presum_multi_kernel(const __grid_constant__ ReduceItems t) {
 
 __global__ void __launch_bounds__(256)
 wgrad_reduce_multi_kernel(const __grid_constant__ ReduceItems t, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][kRedCi * 9 + 1];
   const int i = find_item(t, blockIdx.x);
   const Ub2ReduceItem& it = t.item[i];
@@ -274,10 +287,10 @@ int ub2_pack_conv_weight(const float* w, void* fwd, void* dgrad, int Cout, int C
   __nv_bfloat16* f = static_cast<__nv_bfloat16*>(fwd);
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dgrad);
   const bool full = Cin % kPackT == 0 && Cout % kPackT == 0;
-  if (taps == 9 && full) pack_weight_kernel<9, true><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
-  else if (taps == 9) pack_weight_kernel<9, false><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
-  else if (full) pack_weight_kernel<1, true><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
-  else pack_weight_kernel<1, false><<<grid, 256, 0, st>>>(w, f, d, Cout, Cin, out_scale);
+  if (taps == 9 && full) launch(pack_weight_kernel<9, true>, grid, 256, 0, st, w, f, d, Cout, Cin, out_scale);
+  else if (taps == 9) launch(pack_weight_kernel<9, false>, grid, 256, 0, st, w, f, d, Cout, Cin, out_scale);
+  else if (full) launch(pack_weight_kernel<1, true>, grid, 256, 0, st, w, f, d, Cout, Cin, out_scale);
+  else launch(pack_weight_kernel<1, false>, grid, 256, 0, st, w, f, d, Cout, Cin, out_scale);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -305,15 +318,14 @@ int ub2_wgrad_reduce_multi(const Ub2ReduceItem* items, int n, int accumulate, vo
   red.n = n;
   pre.first_block[pre.n] = pre_blocks;
   red.first_block[n] = red_blocks;
-  if (pre.n > 0) wgrad_presum_multi_kernel<<<pre_blocks, dim3(32, 8), 0, st>>>(pre);
-  wgrad_reduce_multi_kernel<<<red_blocks, dim3(32, kRedCi), 0, st>>>(red, accumulate);
+  if (pre.n > 0) launch(wgrad_presum_multi_kernel, pre_blocks, dim3(32, 8), 0, st, pre);
+  launch(wgrad_reduce_multi_kernel, red_blocks, dim3(32, kRedCi), 0, st, red, accumulate);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_pack_conv_weights_multi(const long long* desc, const int* blocks, int nblocks, void* stream) {
   if (nblocks <= 0) return UB2_ERR_SHAPE;
-  pack_weights_multi_kernel<<<nblocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      desc, reinterpret_cast<const int4*>(blocks));
+  launch(pack_weights_multi_kernel, nblocks, 256, 0, static_cast<cudaStream_t>(stream), desc, reinterpret_cast<const int4*>(blocks));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -324,14 +336,14 @@ int ub2_wgrad_reduce(float* partial, int splits, int Cout, int Cin, int taps, fl
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   if (splits > 8 && total % 4 == 0) {  // many splits: column sums first, all SMs busy
     const long long quads = total / 4;
-    wgrad_presum_kernel<<<static_cast<unsigned>((quads + 31) / 32), dim3(32, 8), 0, st>>>(partial, splits, quads);
+    launch(wgrad_presum_kernel, static_cast<unsigned>((quads + 31) / 32), dim3(32, 8), 0, st, partial, splits, quads);
     splits = 1;
   }
   const dim3 grid((Cout + 31) / 32, (Cin + kRedCi - 1) / kRedCi);
   if (taps == 9)
-    wgrad_reduce_kernel<9><<<grid, dim3(32, kRedCi), 0, st>>>(partial, splits, Cout, Cin, grad, accumulate);
+    launch(wgrad_reduce_kernel<9>, grid, dim3(32, kRedCi), 0, st, partial, splits, Cout, Cin, grad, accumulate);
   else
-    wgrad_reduce_kernel<1><<<grid, dim3(32, kRedCi), 0, st>>>(partial, splits, Cout, Cin, grad, accumulate);
+    launch(wgrad_reduce_kernel<1>, grid, dim3(32, kRedCi), 0, st, partial, splits, Cout, Cin, grad, accumulate);
   return static_cast<int>(cudaGetLastError());
 }
 

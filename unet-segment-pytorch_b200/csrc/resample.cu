@@ -7,6 +7,7 @@
 // (Ho,Wo) output whose remaining border is zero.  Source index arithmetic follows
 // ATen: scale = (in-1)/(out-1) in fp32, src = scale*dst, i0 = int(src), lambda = src-i0.
 // Backward is the exact transpose in gather form (deterministic, no atomics).
+#include "launch.cuh"
 #include "../../include/unetb200.h"
 #include "conv.h"
 #include "resample.cuh"
@@ -24,6 +25,8 @@ struct UpGeom {
 __global__ void __launch_bounds__(256)
 upsample_fwd_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, __nv_bfloat16* __restrict__ out,
                     int ld_out, UpGeom g) {
+  pdl_trigger();
+  pdl_wait();
   const int wo = blockIdx.x * blockDim.y + threadIdx.y;
   const int ho = blockIdx.y;
   const int n = blockIdx.z;
@@ -65,6 +68,8 @@ static constexpr int kStripRows = 16;
 __global__ void __launch_bounds__(256)
 upsample_fwd_strip_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, __nv_bfloat16* __restrict__ out,
                           int ld_out, UpGeom g) {
+  pdl_trigger();
+  pdl_wait();
   const int wo = blockIdx.x * blockDim.y + threadIdx.y;
   const int n = blockIdx.z;
   if (wo >= g.Wo) return;
@@ -142,6 +147,8 @@ static constexpr int kMaxTaps = 8;
 __global__ void __launch_bounds__(256)
 upsample_bwd_kernel(const __nv_bfloat16* __restrict__ dout, int ld_dout,
                     __nv_bfloat16* __restrict__ din, int ld_din, int accumulate, UpGeom g) {
+  pdl_trigger();
+  pdl_wait();
   const int wi = blockIdx.x * blockDim.y + threadIdx.y;
   const int hi = blockIdx.y;
   const int n = blockIdx.z;
@@ -218,6 +225,8 @@ static constexpr int kBT_RH = 24, kBT_RW = 40;   // staged region capacity (rows
 __global__ void __launch_bounds__(256)
 upsample_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ dout, int ld_dout,
                           __nv_bfloat16* __restrict__ din, int ld_din, int accumulate, int slabs, UpGeom g) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ uint4 region[kBT_RH * kBT_RW * 2];
   const int slab = blockIdx.z % slabs;
   const int n = blockIdx.z / slabs;
@@ -320,6 +329,8 @@ static constexpr int kBwdStrip = 16;
 __global__ void __launch_bounds__(256)
 upsample_bwd_strip_kernel(const __nv_bfloat16* __restrict__ dout, int ld_dout, __nv_bfloat16* __restrict__ din,
                           int ld_din, int accumulate, int strip, UpGeom g) {
+  pdl_trigger();
+  pdl_wait();
   const int j = blockIdx.x * blockDim.y + threadIdx.y;   // source column
   const int n = blockIdx.z;
   if (j >= g.win) return;
@@ -431,6 +442,8 @@ static UpGeom up_geom(int N, int hin, int win, int hu, int wu, int Ho, int Wo, i
 // per pixel.
 __global__ void __launch_bounds__(256)
 resize_planes_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int planes, LowRes g) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = static_cast<long long>(planes) * g.Ho * g.Wo;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -453,6 +466,8 @@ resize_planes_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, 
 // Deterministic (ATen scatters with atomics).
 __global__ void __launch_bounds__(256)
 resize_planes_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int planes, LowRes g) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = static_cast<long long>(planes) * g.hin * g.win;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -494,14 +509,12 @@ int ub2_upsample_fwd(const void* in, int ld_in, void* out, int ld_out, int N, in
   if (Ho >= 2 * kStripRows) {
     const dim3 sblock = up_block(g.cgs);
     const dim3 sgrid((Wo + sblock.y - 1) / sblock.y, (Ho + kStripRows - 1) / kStripRows, N);
-    upsample_fwd_strip_kernel<<<sgrid, sblock, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, g);
+    launch(upsample_fwd_strip_kernel, sgrid, sblock, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, g);
     return static_cast<int>(cudaGetLastError());
   }
   const dim3 block = up_block(g.cgs);
   const dim3 grid((Wo + block.y - 1) / block.y, Ho, N);
-  upsample_fwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, g);
+  launch(upsample_fwd_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(in), ld_in, static_cast<__nv_bfloat16*>(out), ld_out, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -517,32 +530,25 @@ int ub2_upsample_bwd(const void* dout, int ld_dout, void* din, int ld_din, int a
     int strip = kBwdStrip;
     while (strip > 2 && static_cast<long long>(N) * ((hin + strip - 1) / strip) * win * g.cgs < wave) strip >>= 1;
     const dim3 sgrid((win + sblock.y - 1) / sblock.y, (hin + strip - 1) / strip, N);
-    upsample_bwd_strip_kernel<<<sgrid, sblock, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din, accumulate,
-        strip, g);
+    launch(upsample_bwd_strip_kernel, sgrid, sblock, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din, accumulate, strip, g);
     return static_cast<int>(cudaGetLastError());
   }
   if (bwd_tiled_ok(g)) {
     const int slabs = C / 16;
     const dim3 tgrid((win + kBT_W - 1) / kBT_W, (hin + kBT_H - 1) / kBT_H, N * slabs);
-    upsample_bwd_tiled_kernel<<<tgrid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din,
-        accumulate, slabs, g);
+    launch(upsample_bwd_tiled_kernel, tgrid, 256, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din, accumulate, slabs, g);
     return static_cast<int>(cudaGetLastError());
   }
   const dim3 block = up_block(g.cgs);
   const dim3 grid((win + block.y - 1) / block.y, hin, N);
-  upsample_bwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din,
-      accumulate, g);
+  launch(upsample_bwd_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(dout), ld_dout, static_cast<__nv_bfloat16*>(din), ld_din, accumulate, g);
   return static_cast<int>(cudaGetLastError());
 }
 
 int ub2_resize_planes_fwd(const float* in, float* out, int planes, int hin, int win, int Ho, int Wo, void* stream) {
   if (planes <= 0 || hin <= 0 || win <= 0 || Ho <= 0 || Wo <= 0) return UB2_ERR_SHAPE;
   const long long total = static_cast<long long>(planes) * Ho * Wo;
-  resize_planes_fwd_kernel<<<stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in, out, planes, make_lowres(hin, win, Ho, Wo));
+  launch(resize_planes_fwd_kernel, stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream), in, out, planes, make_lowres(hin, win, Ho, Wo));
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -550,8 +556,7 @@ int ub2_resize_planes_bwd(const float* dout, float* din, int planes, int hin, in
                           void* stream) {
   if (planes <= 0 || hin <= 0 || win <= 0 || Ho <= 0 || Wo <= 0) return UB2_ERR_SHAPE;
   const long long total = static_cast<long long>(planes) * hin * win;
-  resize_planes_bwd_kernel<<<stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dout, din, planes, make_lowres(hin, win, Ho, Wo));
+  launch(resize_planes_bwd_kernel, stream_grid(total, 256, num_sms(), 8), 256, 0, static_cast<cudaStream_t>(stream), dout, din, planes, make_lowres(hin, win, Ho, Wo));
   return static_cast<int>(cudaGetLastError());
 }
 
