@@ -140,6 +140,25 @@ int ub2_upsample_fwd(const void* in, int ld_in, void* out, int ld_out, int N, in
 int ub2_upsample_bwd(const void* dout, int ld_dout, void* din, int ld_din, int accumulate, int N,
                      int hin, int win, int hu, int wu, int Ho, int Wo, int C, void* stream);
 
+/* ConvTranspose2d(C, C/2, 2, stride 2) + F.pad (unet/models/layers.py:81, :98-102, :217-221): the transposed
+ * convolution itself is ub2_conv_fwd with the (4*Cout, Cin) reshaped weight (row (i,j,co)) and the bias in its
+ * epilogue; these are the pixel shuffle out[n, 2y+i+py, 2x+j+px, co] = t[n, y, x, (i*2+j)*C + co] with the
+ * padding of F.pad (zeros), its transpose, and the bias gradient: dbias[co] += sum of the gathered dout.
+ * `partials`: (rows, C) doubles with rows = ub2_shuffle2x2_rows(...); pass NULL to skip the bias gradient. */
+int ub2_shuffle2x2_fwd(const void* t, int ld_t, void* out, int ld_out, int N, int h, int w, int C, int Ho, int Wo,
+                       void* stream);
+int ub2_shuffle2x2_rows(int N, int h, int w, int C, int Ho, int Wo);
+int ub2_shuffle2x2_bwd(const void* dout, int ld_dout, void* dt, int ld_dt, double* partials, int rows, float* dbias,
+                       int N, int h, int w, int C, int Ho, int Wo, void* stream);
+/* The (Cin, Cout, 2, 2) fp32 ConvTranspose2d parameter as 1x1-convolution packs: fwd (4*Cout, Cin) bf16 with row
+ * (i*2+j)*Cout + co, dg (Cin, 4*Cout) bf16, and the epilogue vectors scale4 = 1, shift4 = bias tiled four times
+ * (each 4*Cout floats; bias may be NULL).  Any output pointer may be NULL. */
+int ub2_pack_convt_weight(const float* w, const float* bias, void* fwd, void* dg, float* scale4, float* shift4,
+                          int Cin, int Cout, void* stream);
+/* grad (Cin, Cout, 2, 2) fp32 = (or +=) the split-K partials (splits, Cin, 4*Cout) of ub2_conv_wgrad(taps = 1) on
+ * the shuffled gradient, summed in a fixed order. */
+int ub2_convt_wgrad_reduce(const float* partial, int splits, int Cin, int Cout, float* grad, int accumulate,
+                           void* stream);
 /* F.interpolate(x, size, mode='bilinear', align_corners=True) of the deep-supervision logits
  * (unet/models/unet.py:206-208) and its transpose in gather form (deterministic): fp32 NCHW,
  * planes = N * channels, (hin,win) -> (Ho,Wo), any scale. */

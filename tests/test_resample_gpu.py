@@ -76,3 +76,45 @@ def test_resize_logits_fwd_bwd(n, c, h, w, ho, wo):
     assert torch.allclose(xo.grad, xr.grad, rtol=1e-4, atol=1e-5 * scale)
     out2 = ops.resize_logits(x, (ho, wo))
     assert torch.equal(out2, out.detach())
+
+
+@pytest.mark.parametrize("n,cin,h,w,ho,wo", [(2, 128, 8, 8, 16, 16), (1, 64, 6, 9, 13, 19), (2, 256, 16, 16, 32, 32)])
+def test_conv_transpose2x2_and_pad_vs_torch(n, cin, h, w, ho, wo):
+    """nn.ConvTranspose2d(C, C/2, 2, 2) + F.pad (layers.py:81, :98-102) as a tensor-core 1x1 convolution +
+    the pixel-shuffle kernels of csrc/shuffle.cu: output, input gradient, weight gradient and bias gradient
+    against torch's fp32 transposed convolution of the same bf16-rounded operands."""
+    import torch.nn.functional as F
+    from unet import ops
+
+    cout = cin // 2
+    g = torch.Generator().manual_seed(cin + h)
+    x = torch.randn(n, cin, h, w, generator=g).bfloat16().float()
+    wt = (torch.randn(cin, cout, 2, 2, generator=g) / cin ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g)
+    dy = torch.randn(n, cout, ho, wo, generator=g).bfloat16().float()
+
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = F.conv_transpose2d(xr, wr, br, stride=2)
+    py, px = ho - 2 * h, wo - 2 * w
+    y = F.pad(y, [px // 2, px - px // 2, py // 2, py - py // 2])
+    y.backward(dy)
+
+    xc = x.cuda().requires_grad_(True)
+    wc = wt.cuda().requires_grad_(True)
+    bc = b.cuda().requires_grad_(True)
+    out = ops.conv_transpose2x2(xc, wc, bc, ho, wo)
+    assert out.shape == (n, cout, ho, wo)
+    out.backward(dy.cuda().to(out.dtype))
+
+    def rel(a, r):
+        return ((a.float().cpu() - r).norm() / (r.norm() + 1e-12)).item()
+
+    assert rel(out, y.detach()) <= 4e-3            # bf16 storage of the result
+    assert rel(xc.grad, xr.grad) <= 4e-3
+    assert rel(wc.grad, wr.grad) <= 1e-3           # fp32 accumulation of bf16 products
+    assert rel(bc.grad, br.grad) <= 1e-4           # sums of bf16 values in fp32 / fp64
+    # the padding ring is exactly zero
+    if py or px:
+        mask = torch.ones(ho, wo, dtype=torch.bool)
+        mask[py // 2: py // 2 + 2 * h, px // 2: px // 2 + 2 * w] = False
+        assert (out.float().cpu()[:, :, mask] == 0).all()

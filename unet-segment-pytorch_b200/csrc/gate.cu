@@ -20,6 +20,10 @@
 #include "resample.cuh"
 #include "vec.cuh"
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 namespace ub2 {
 
 static constexpr int kGateThreads = 256;
@@ -123,82 +127,177 @@ __device__ __forceinline__ void block_reduce_scalars(float (&acc)[NS], double* o
 // Strip walk for the passes that need up(q): a block owns `slots` columns x kGateStrip rows of one
 // image, a thread one column (x `tpp` lanes over the channels) and walks the rows.  No per-pixel
 // integer division, and the two horizontally interpolated low-resolution rows a destination row lies
-// between stay in registers (they change every other row for a 2x up-sampling).  ncu on the
-// per-pixel form: ~320 instructions per pixel-vector, half of them integer address arithmetic.
-template <int G>
-struct QRoll {
-  int cur0, cur1, w0, w1;
+// between stay in registers (they change every other row for a 2x up-sampling).
+//
+// Every operand of a row is fetched with cp.async into a per-thread ring in shared memory kD rows ahead:
+// the round-1 form of these kernels issued one 16-byte load per thread and row and used it at once —
+// 8-12 KB in flight per SM where HBM needs ~35 KB (ncu: long-scoreboard stalls, 0.9-2.7 TB/s, 23-32 %
+// occupancy because the prefetch that was tried lived in registers).  A thread only ever reads what it
+// fetched itself, so cp.async.wait_group is all the synchronisation the ring needs.
+//   qbuf [QR][2][G][threads] uint4   low-resolution rows (columns w0 / w1 of this thread), row h in slot h % QR
+//   vbuf [kD][NV][G][threads] uint4  streamed bf16 vectors of an output row (stage ho % kD)
+//   sbuf [kD][NS][threads]   float   streamed per-pixel scalars
+// Low-resolution rows are requested together with the first output row that needs them, so one
+// wait_group per output row covers both.  QR = 4 holds every row in flight for up-sampling factors >= 2
+// (H >= 2*hin - 1, the U-Net case), QR = 8 for factors >= 1.
+static constexpr int kD = 4;   // output rows in flight per thread
+#ifndef UB2_GATE_BWD_S_BLOCKS
+#define UB2_GATE_BWD_S_BLOCKS 2   // 3 caps gate_bwd_s at 80 registers (small spill); A/B on the GPU decides
+#endif
+
+__device__ __forceinline__ void cp_async16_ca(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int G, int QR, int NV, int NS>
+struct Strip {
+  static constexpr int kQVecs = QR * 2 * G;
+  static constexpr int kVVecs = kD * NV * G;
+  static constexpr size_t kBytes = static_cast<size_t>(kGateThreads) * (16 * (kQVecs + kVVecs) + 4 * kD * NS);
+  // thread -> (column, channel group)
+  int slot, j, n, wo, ho0, ho1;
+  bool pv;
+  // low-resolution roll
+  int cur0, cur1, w0, w1, qnext;
   float a0, a1, b0, b1;
   F8 top[G], bot[G];
-};
-template <int G>
-__device__ __forceinline__ void qroll_init(QRoll<G>& r, const GateGeom& g, int wo) {
-  r.cur0 = r.cur1 = -1;
-  src_index(g.lr.rw, wo < g.W ? wo : g.W - 1, g.lr.win, r.w0, r.w1, r.b0, r.b1);
+  uint4* qbuf;
+  uint4* vbuf;
+  float* sbuf;
+
+  __device__ __forceinline__ void init(const GateGeom& g, uint8_t* smem) {
+    slot = threadIdx.x / g.tpp;
+    j = threadIdx.x % g.tpp;
+    const int bw = static_cast<int>(blockIdx.x) % g.wt;
+    const int bh = (static_cast<int>(blockIdx.x) / g.wt) % g.ht;
+    n = static_cast<int>(blockIdx.x) / (g.wt * g.ht);
+    wo = bw * g.slots + slot;
+    pv = wo < g.W;
+    ho0 = bh * kGateStrip;
+    ho1 = min(ho0 + kGateStrip, g.H);
+    cur0 = cur1 = -1;
+    src_index(g.lr.rw, pv ? wo : g.W - 1, g.lr.win, w0, w1, b0, b1);
+    int h0, h1;
+    float l0, l1;
+    src_index(g.lr.rh, ho0, g.lr.hin, h0, h1, l0, l1);
+    qnext = h0;
+    qbuf = reinterpret_cast<uint4*>(smem);
+    vbuf = qbuf + kQVecs * kGateThreads;
+    sbuf = reinterpret_cast<float*>(vbuf + kVVecs * kGateThreads);
 #pragma unroll
-  for (int gi = 0; gi < G; ++gi)
+    for (int gi = 0; gi < G; ++gi)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r.top[gi].v[k] = r.bot[gi].v[k] = 0.f;
-}
-template <int G>
-__device__ __forceinline__ void qroll_row(QRoll<G>& r, const __nv_bfloat16* __restrict__ q, int ld_q,
-                                          const GateGeom& g, int n, int ho, int j, bool colv) {
-  int h0, h1;
-  src_index(g.lr.rh, ho, g.lr.hin, h0, h1, r.a0, r.a1);   // block-uniform
-  const __nv_bfloat16* base = q + static_cast<size_t>(n) * g.lr.hin * g.lr.win * ld_q;
-  auto hrow = [&](int h, int gi) {
-    F8 o;
-    const int cg = j + gi * g.tpp;
-    if (colv && cg < g.cgs) {
-      const F8 a = load8(base + (static_cast<size_t>(h) * g.lr.win + r.w0) * ld_q + cg * 8);
-      const F8 b = load8(base + (static_cast<size_t>(h) * g.lr.win + r.w1) * ld_q + cg * 8);
+      for (int k = 0; k < 8; ++k) top[gi].v[k] = bot[gi].v[k] = 0.f;
+  }
+  __device__ __forceinline__ bool lane_on(const GateGeom& g, int gi) const { return pv && (j + gi * g.tpp) < g.cgs; }
+
+  // Request everything output row `ho` needs (its own commit group; an empty one past the strip).
+  // vptr[v]: row-0 pointer of streamed tensor v at this thread's column / first channel group; sptr likewise.
+  __device__ __forceinline__ void request(const GateGeom& g, int ho, const __nv_bfloat16* __restrict__ q, int ld_q,
+                                          const __nv_bfloat16* const (&vptr)[NV > 0 ? NV : 1], const int (&vld)[NV > 0 ? NV : 1],
+                                          const float* const (&sptr)[NS > 0 ? NS : 1]) {
+    if (ho < ho1) {
+      int h0, h1;
+      float l0, l1;
+      src_index(g.lr.rh, ho, g.lr.hin, h0, h1, l0, l1);
+      const __nv_bfloat16* qimg = q + static_cast<size_t>(n) * g.lr.hin * g.lr.win * ld_q;
+      for (; qnext <= h1; ++qnext) {
+        uint4* dst = qbuf + static_cast<size_t>((qnext % QR) * 2 * G) * kGateThreads + threadIdx.x;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = r.b0 * a.v[k] + r.b1 * b.v[k];
-    } else {
+        for (int gi = 0; gi < G; ++gi) {
+          if (lane_on(g, gi)) {
+            const int cg = j + gi * g.tpp;
+            cp_async16_ca(dst + (0 * G + gi) * kGateThreads, qimg + (static_cast<size_t>(qnext) * g.lr.win + w0) * ld_q + cg * 8);
+            cp_async16_ca(dst + (1 * G + gi) * kGateThreads, qimg + (static_cast<size_t>(qnext) * g.lr.win + w1) * ld_q + cg * 8);
+          }
+        }
+      }
+      const size_t pix = (static_cast<size_t>(n) * g.H + ho) * g.W + (pv ? wo : 0);
+      const int st = ho % kD;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+      for (int v = 0; v < NV; ++v) {
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) {
+          if (lane_on(g, gi))
+            cp_async16_cg(vbuf + static_cast<size_t>((st * NV + v) * G + gi) * kGateThreads + threadIdx.x,
+                          vptr[v] + pix * vld[v] + (j + gi * g.tpp) * 8);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NS; ++k) {
+        if (pv) cp_async4(sbuf + static_cast<size_t>(st * NS + k) * kGateThreads + threadIdx.x, sptr[k] + pix);
+      }
     }
-    return o;
-  };
-  if (h0 != r.cur0) {
-#pragma unroll
-    for (int gi = 0; gi < G; ++gi) r.top[gi] = (h0 == r.cur1) ? r.bot[gi] : hrow(h0, gi);
-    r.cur0 = h0;
+    cp_async_commit();
   }
-  if (h1 != r.cur1) {
+
+  // After the wait for row `ho`: advance the roll to the two low-resolution rows it lies between.
+  __device__ __forceinline__ void roll_to(const GateGeom& g, int ho) {
+    int h0, h1;
+    src_index(g.lr.rh, ho, g.lr.hin, h0, h1, a0, a1);   // block-uniform
+    auto hrow = [&](int h, int gi) {
+      F8 o;
+      if (lane_on(g, gi)) {
+        const uint4* src = qbuf + static_cast<size_t>((h % QR) * 2 * G) * kGateThreads + threadIdx.x;
+        const F8 a = unpack8(src[(0 * G + gi) * kGateThreads]);
+        const F8 b = unpack8(src[(1 * G + gi) * kGateThreads]);
 #pragma unroll
-    for (int gi = 0; gi < G; ++gi) r.bot[gi] = (h1 == r.cur0) ? r.top[gi] : hrow(h1, gi);
-    r.cur1 = h1;
+        for (int k = 0; k < 8; ++k) o.v[k] = b0 * a.v[k] + b1 * b.v[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = 0.f;
+      }
+      return o;
+    };
+    if (h0 != cur0) {
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) top[gi] = (h0 == cur1) ? bot[gi] : hrow(h0, gi);
+      cur0 = h0;
+    }
+    if (h1 != cur1) {
+#pragma unroll
+      for (int gi = 0; gi < G; ++gi) bot[gi] = (h1 == cur0) ? top[gi] : hrow(h1, gi);
+      cur1 = h1;
+    }
   }
-}
-template <int G>
-__device__ __forceinline__ F8 qroll_get(const QRoll<G>& r, int gi) {
-  F8 u;
+  __device__ __forceinline__ F8 up(int gi) const {
+    F8 u;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) u.v[k] = r.a0 * r.top[gi].v[k] + r.a1 * r.bot[gi].v[k];
-  return u;
-}
+    for (int k = 0; k < 8; ++k) u.v[k] = a0 * top[gi].v[k] + a1 * bot[gi].v[k];
+    return u;
+  }
+  __device__ __forceinline__ F8 vec(int ho, int v, int gi) const {
+    return unpack8(vbuf[static_cast<size_t>(((ho % kD) * NV + v) * G + gi) * kGateThreads + threadIdx.x]);
+  }
+  __device__ __forceinline__ float scalar(int ho, int k) const {
+    return sbuf[static_cast<size_t>((ho % kD) * NS + k) * kGateThreads + threadIdx.x];
+  }
+};
 
-// for (row of the strip) { pix, pv, u = up(q) at this pixel via qroll_get(roll, gi) }
-#define GATE_STRIP_LOOP(g, G_)                                                               \
-  const int slot = threadIdx.x / (g).tpp;                                                    \
-  const int j = threadIdx.x % (g).tpp;                                                       \
-  const int bw_ = static_cast<int>(blockIdx.x) % (g).wt;                                     \
-  const int bh_ = (static_cast<int>(blockIdx.x) / (g).wt) % (g).ht;                          \
-  const int n = static_cast<int>(blockIdx.x) / ((g).wt * (g).ht);                            \
-  const int wo = bw_ * (g).slots + slot;                                                     \
-  const bool pv = wo < (g).W;                                                                \
-  QRoll<G_> roll;                                                                            \
-  qroll_init<G_>(roll, g, wo);                                                               \
-  const int ho_end_ = min((bh_ + 1) * kGateStrip, (g).H);                                    \
-  for (int ho = bh_ * kGateStrip; ho < ho_end_; ++ho)
-
-#define GATE_STRIP_ROW(g, G_)                                                                \
-  const int pix = (n * (g).H + ho) * (g).W + (pv ? wo : 0);                                  \
-  qroll_row<G_>(roll, q, ld_q, g, n, ho, j, pv);
+// for (row of the strip) { requests kD-1 rows ahead; waits for this row; rolls }: the body sees
+// `ho`, `pix` and the Strip `S` with up(q) / streamed vectors of the row.
+#define GATE_STRIP_BEGIN(S, g, q, ld_q, vptr, vld, sptr)                                       \
+  extern __shared__ __align__(16) uint8_t strip_smem[];                                        \
+  S.init(g, strip_smem);                                                                       \
+  _Pragma("unroll") for (int pre = 0; pre < kD - 1; ++pre) S.request(g, S.ho0 + pre, q, ld_q, vptr, vld, sptr); \
+  for (int ho = S.ho0; ho < S.ho1; ++ho) {                                                     \
+    S.request(g, ho + kD - 1, q, ld_q, vptr, vld, sptr);                                       \
+    cp_async_wait<kD - 1>();                                                                   \
+    S.roll_to(g, ho);                                                                          \
+    const int pix = (S.n * (g).H + ho) * (g).W + (S.pv ? S.wo : 0);
+#define GATE_STRIP_END }
 
 // ------------------------------------------------------------------------------ forward
-template <int G>
+template <int G, int QR>
 __global__ void __launch_bounds__(kGateThreads)
 gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* partials, GateGeom g) {
   pdl_trigger();
@@ -211,14 +310,16 @@ gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* parti
     for (int b = 0; b < 2; ++b)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[a][b][k] = 0.f;
-  GATE_STRIP_LOOP(g, G) {
-    GATE_STRIP_ROW(g, G)
+  Strip<G, QR, 0, 0> S;
+  const __nv_bfloat16* const vptr[1] = {nullptr};
+  const int vld[1] = {0};
+  const float* const sptr[1] = {nullptr};
+  GATE_STRIP_BEGIN(S, g, q, ld_q, vptr, vld, sptr)
     (void)pix;
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-      const int cg = j + gi * g.tpp;
-      if (pv && cg < g.cgs) {
-        const F8 u = qroll_get<G>(roll, gi);
+      if (S.lane_on(g, gi)) {
+        const F8 u = S.up(gi);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           acc[gi][0][k] += u.v[k];
@@ -226,31 +327,40 @@ gate_upstats_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, double* parti
         }
       }
     }
-  }
-  const int slot2 = threadIdx.x / g.tpp, j2 = threadIdx.x % g.tpp;
-  block_reduce_channels<G, 2>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 2 * g.C, smem);
+  GATE_STRIP_END
+  block_reduce_channels<G, 2>(acc, g, S.slot, S.j, partials + static_cast<size_t>(blockIdx.x) * 2 * g.C, smem);
 }
 
-// Per-channel coefficient vectors of the thread's first channel group, kept in registers
-// (the thread -> channel-group mapping is fixed); further groups (Ci > 256) read through L1.
-struct GateVec {
-  F8 sg, sx, h, w;
+// Per-channel coefficient vectors (BN_g scale, BN_x scale, summed shifts, psi weights) live in shared
+// memory: 32 registers per thread in the round-1 form, which is what kept these kernels at two or three
+// blocks per SM.  A warp reads at most `tpp` distinct 32-byte rows of it at a time (broadcast).
+struct GateCoef {
+  const float* sg;   // [C] each, contiguous: sg | sx | h | w
+  __device__ __forceinline__ F8 get(int which, int cg, int C) const {
+    F8 r;
+    const float4* p = reinterpret_cast<const float4*>(sg + which * C + cg * 8);
+    const float4 a = p[0], b = p[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
 };
-__device__ __forceinline__ GateVec gate_vec(const float* sg, const float* hg, const float* sx,
-                                            const float* hx, const float* wpsi, int cg, int cgs) {
-  GateVec v;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = (cg < cgs ? cg : 0) * 8 + k;
-    v.sg.v[k] = __ldg(sg + c);
-    v.sx.v[k] = __ldg(sx + c);
-    v.h.v[k] = __ldg(hg + c) + __ldg(hx + c);
-    v.w.v[k] = __ldg(wpsi + c);
+// s_coef: 4*C floats of (dynamic) shared memory behind the strip ring; call before the strip loop
+__device__ __forceinline__ GateCoef gate_coef_load(float* s_coef, const float* sg, const float* hg, const float* sx,
+                                                   const float* hx, const float* wpsi, int C) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_coef[c] = __ldg(sg + c);
+    s_coef[C + c] = __ldg(sx + c);
+    s_coef[2 * C + c] = __ldg(hg + c) + __ldg(hx + c);
+    s_coef[3 * C + c] = __ldg(wpsi + c);
   }
-  return v;
+  __syncthreads();
+  GateCoef k;
+  k.sg = s_coef;
+  return k;
 }
 
-template <int G>
+template <int G, int QR>
 __global__ void __launch_bounds__(kGateThreads)
 gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat16* __restrict__ xp,
                 int ld_xp, const float* __restrict__ sg, const float* __restrict__ hg,
@@ -261,31 +371,36 @@ gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat
   pdl_wait();
   __shared__ float smem[kGateThreads / 32];
   float st[2] = {0.f, 0.f};
-  const GateVec v0 = gate_vec(sg, hg, sx, hx, wpsi, threadIdx.x % g.tpp, g.cgs);
-  GATE_STRIP_LOOP(g, G) {
-    GATE_STRIP_ROW(g, G)
+  typedef Strip<G, QR, 1, 0> S_t;
+  S_t S;
+  const __nv_bfloat16* const vptr[1] = {xp};
+  const int vld[1] = {ld_xp};
+  const float* const sptr[1] = {nullptr};
+  extern __shared__ __align__(16) uint8_t strip_smem_c[];
+  const GateCoef cf = gate_coef_load(reinterpret_cast<float*>(strip_smem_c + S_t::kBytes), sg, hg, sx, hx, wpsi, g.C);
+  GATE_STRIP_BEGIN(S, g, q, ld_q, vptr, vld, sptr)
     float dot = 0.f;
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-      const int cg = j + gi * g.tpp;
-      if (pv && cg < g.cgs) {
-        const GateVec v = (gi == 0) ? v0 : gate_vec(sg, hg, sx, hx, wpsi, cg, g.cgs);
-        const F8 u = qroll_get<G>(roll, gi);
-        const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
+      if (S.lane_on(g, gi)) {
+        const int cg = S.j + gi * g.tpp;
+        const F8 u = S.up(gi);
+        const F8 xv = S.vec(ho, 0, gi);
+        const F8 vsg = cf.get(0, cg, g.C), vsx = cf.get(1, cg, g.C), vh = cf.get(2, cg, g.C), vw = cf.get(3, cg, g.C);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float t = fmaf(u.v[k], v.sg.v[k], fmaf(xv.v[k], v.sx.v[k], v.h.v[k]));
-          dot = fmaf(v.w.v[k], fmaxf(t, 0.f), dot);
+          const float t = fmaf(u.v[k], vsg.v[k], fmaf(xv.v[k], vsx.v[k], vh.v[k]));
+          dot = fmaf(vw.v[k], fmaxf(t, 0.f), dot);
         }
       }
     }
     dot = group_sum(dot, g.tpp);
-    if (pv && j == 0) {
+    if (S.pv && S.j == 0) {
       psi_raw[pix] = dot;
       st[0] += dot;
       st[1] = fmaf(dot, dot, st[1]);
     }
-  }
+  GATE_STRIP_END
   if (partials != nullptr) block_reduce_scalars<2>(st, partials + static_cast<size_t>(blockIdx.x) * 2, smem);
 }
 
@@ -375,8 +490,8 @@ gate_bwd_a_kernel(const __nv_bfloat16* __restrict__ dout, int ld_do, const __nv_
 
 // ds_c = dpsi_raw * w_psi_c * [t_c > 0]; channel sums (raw, the finalize converts them):
 // sum ds, sum ds*xp, sum ds*up(q), sum dpsi_raw*relu(t)
-template <int G>
-__global__ void __launch_bounds__(kGateThreads)
+template <int G, int QR>
+__global__ void __launch_bounds__(kGateThreads, G == 1 ? UB2_GATE_BWD_S_BLOCKS : 1)
 gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi_raw,
                   const float* __restrict__ coef_psi, const __nv_bfloat16* __restrict__ q, int ld_q,
                   const __nv_bfloat16* __restrict__ xp, int ld_xp, const float* __restrict__ sg,
@@ -387,7 +502,6 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
   pdl_wait();
   __shared__ float smem[kGateThreads * 8];
   const float cA = __ldg(coef_psi), cB = __ldg(coef_psi + 1), cC = __ldg(coef_psi + 2);
-  const GateVec v0 = gate_vec(sg, hg, sx, hx, wpsi, threadIdx.x % g.tpp, g.cgs);
   float acc[G][4][8];
 #pragma unroll
   for (int a = 0; a < G; ++a)
@@ -395,22 +509,28 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
     for (int b = 0; b < 4; ++b)
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[a][b][k] = 0.f;
-  GATE_STRIP_LOOP(g, G) {
-    GATE_STRIP_ROW(g, G)
+  typedef Strip<G, QR, 1, 2> S_t;
+  S_t S;
+  const __nv_bfloat16* const vptr[1] = {xp};
+  const int vld[1] = {ld_xp};
+  const float* const sptr[2] = {dpsin, psi_raw};
+  extern __shared__ __align__(16) uint8_t strip_smem_c[];
+  const GateCoef cf = gate_coef_load(reinterpret_cast<float*>(strip_smem_c + S_t::kBytes), sg, hg, sx, hx, wpsi, g.C);
+  GATE_STRIP_BEGIN(S, g, q, ld_q, vptr, vld, sptr)
     // BN_psi backward: d psi_raw = A*dn + B*psi_raw + C
-    const float dpr = pv ? fmaf(cA, __ldg(dpsin + pix), fmaf(cB, __ldg(psi_raw + pix), cC)) : 0.f;
+    const float dpr = S.pv ? fmaf(cA, S.scalar(ho, 0), fmaf(cB, S.scalar(ho, 1), cC)) : 0.f;
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-      const int cg = j + gi * g.tpp;
-      if (pv && cg < g.cgs) {
-        const GateVec v = (gi == 0) ? v0 : gate_vec(sg, hg, sx, hx, wpsi, cg, g.cgs);
-        const F8 u = qroll_get<G>(roll, gi);
-        const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
+      if (S.lane_on(g, gi)) {
+        const int cg = S.j + gi * g.tpp;
+        const F8 u = S.up(gi);
+        const F8 xv = S.vec(ho, 0, gi);
+        const F8 vsg = cf.get(0, cg, g.C), vsx = cf.get(1, cg, g.C), vh = cf.get(2, cg, g.C), vw = cf.get(3, cg, g.C);
         F8 o;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float t = fmaf(u.v[k], v.sg.v[k], fmaf(xv.v[k], v.sx.v[k], v.h.v[k]));
-          const float d = (t > 0.f) ? dpr * v.w.v[k] : 0.f;
+          const float t = fmaf(u.v[k], vsg.v[k], fmaf(xv.v[k], vsx.v[k], vh.v[k]));
+          const float d = (t > 0.f) ? dpr * vw.v[k] : 0.f;
           o.v[k] = d;
           acc[gi][0][k] += d;
           acc[gi][1][k] = fmaf(d, xv.v[k], acc[gi][1][k]);
@@ -420,9 +540,8 @@ gate_bwd_s_kernel(const float* __restrict__ dpsin, const float* __restrict__ psi
         store8(ds + static_cast<size_t>(pix) * ld_ds + cg * 8, o);
       }
     }
-  }
-  const int slot2 = threadIdx.x / g.tpp, j2 = threadIdx.x % g.tpp;
-  block_reduce_channels<G, 4>(acc, g, slot2, j2, partials + static_cast<size_t>(blockIdx.x) * 4 * g.C, smem);
+  GATE_STRIP_END
+  block_reduce_channels<G, 4>(acc, g, S.slot, S.j, partials + static_cast<size_t>(blockIdx.x) * 4 * g.C, smem);
 }
 
 // Raw sums -> parameter gradients and the backward coefficients of the two BatchNorms:
@@ -465,7 +584,7 @@ __global__ void gate_bwd_finalize_kernel(const double* __restrict__ partials, in
 }
 
 // dxp = BN_x backward of ds; dgup = BN_g backward of ds (full resolution, later up-sample^T)
-template <int G>
+template <int G, int QR>
 __global__ void __launch_bounds__(kGateThreads)
 gate_bwd_xg_kernel(const __nv_bfloat16* __restrict__ ds, int ld_ds, const __nv_bfloat16* __restrict__ xp,
                    int ld_xp, const __nv_bfloat16* __restrict__ q, int ld_q,
@@ -473,42 +592,95 @@ gate_bwd_xg_kernel(const __nv_bfloat16* __restrict__ ds, int ld_ds, const __nv_b
                    __nv_bfloat16* __restrict__ dgup, int ld_dg, GateGeom g) {
   pdl_trigger();
   pdl_wait();
-  F8 cf[6];
-  {
-    const int cg0 = threadIdx.x % g.tpp;
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) cf[r].v[k] = __ldg(coef + r * g.C + (cg0 < g.cgs ? cg0 : 0) * 8 + k);
-  }
-  GATE_STRIP_LOOP(g, G) {
-    GATE_STRIP_ROW(g, G)
+  typedef Strip<G, QR, 2, 0> S_t;
+  S_t S;
+  const __nv_bfloat16* const vptr[2] = {ds, xp};
+  const int vld[2] = {ld_ds, ld_xp};
+  const float* const sptr[1] = {nullptr};
+  // the six coefficient rows of gate_bwd_finalize in shared memory (6*C floats behind the ring)
+  extern __shared__ __align__(16) uint8_t strip_smem_c[];
+  float* s_cf = reinterpret_cast<float*>(strip_smem_c + S_t::kBytes);
+  for (int c = threadIdx.x; c < 6 * g.C; c += blockDim.x) s_cf[c] = __ldg(coef + c);
+  __syncthreads();
+  GateCoef cf;
+  cf.sg = s_cf;
+  GATE_STRIP_BEGIN(S, g, q, ld_q, vptr, vld, sptr)
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-      const int cg = j + gi * g.tpp;
-      if (pv && cg < g.cgs) {
-        const F8 d = load8_stream(ds + static_cast<size_t>(pix) * ld_ds + cg * 8);
-        const F8 xv = load8_stream(xp + static_cast<size_t>(pix) * ld_xp + cg * 8);
-        const F8 u = qroll_get<G>(roll, gi);
+      if (S.lane_on(g, gi)) {
+        const int cg = S.j + gi * g.tpp;
+        const F8 d = S.vec(ho, 0, gi);
+        const F8 xv = S.vec(ho, 1, gi);
+        const F8 u = S.up(gi);
         F8 ox, og;
+        {
+          const F8 c0 = cf.get(0, cg, g.C), c1 = cf.get(1, cg, g.C), c2 = cf.get(2, cg, g.C);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (gi == 0) {
-            ox.v[k] = fmaf(cf[0].v[k], d.v[k], fmaf(cf[1].v[k], xv.v[k], cf[2].v[k]));
-            og.v[k] = fmaf(cf[3].v[k], d.v[k], fmaf(cf[4].v[k], u.v[k], cf[5].v[k]));
-          } else {
-            const int c = cg * 8 + k;
-            ox.v[k] = fmaf(__ldg(coef + c), d.v[k], fmaf(__ldg(coef + g.C + c), xv.v[k], __ldg(coef + 2 * g.C + c)));
-            og.v[k] = fmaf(__ldg(coef + 3 * g.C + c), d.v[k],
-                           fmaf(__ldg(coef + 4 * g.C + c), u.v[k], __ldg(coef + 5 * g.C + c)));
-          }
+          for (int k = 0; k < 8; ++k) ox.v[k] = fmaf(c0.v[k], d.v[k], fmaf(c1.v[k], xv.v[k], c2.v[k]));
+        }
+        {
+          const F8 c3 = cf.get(3, cg, g.C), c4 = cf.get(4, cg, g.C), c5 = cf.get(5, cg, g.C);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) og.v[k] = fmaf(c3.v[k], d.v[k], fmaf(c4.v[k], u.v[k], c5.v[k]));
         }
         store8(dxp + static_cast<size_t>(pix) * ld_dxp + cg * 8, ox);
         store8(dgup + static_cast<size_t>(pix) * ld_dg + cg * 8, og);
       }
     }
-  }
+  GATE_STRIP_END
 }
+
+// ---- launch helpers of the strip kernels
+// Ring size of the low-resolution rows: rows h0(ho) .. h1(ho + kD - 1) are alive at once, i.e.
+// floor((kD-1) * rh) + 3 of them (rh = (hin-1)/(H-1)); 4 slots cover every up-sampling factor >= 1.5
+// (the U-Net's 2x), 8 slots every factor > 0.5.  Down-sampling gates are not an attention-gate geometry.
+static int strip_qr(const GateGeom& g) {
+  const int alive = static_cast<int>((kD - 1) * static_cast<double>(g.lr.rh) + 1e-4) + 3;
+  if (alive <= 4) return 4;
+  if (alive <= 8) return 8;
+  return 0;
+}
+// Opt in to > 48 KB of dynamic shared memory once per (kernel, device).
+static int strip_smem_attr(const void* fn, size_t bytes) {
+  if (bytes <= 48 * 1024) return 0;
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  const int dev = device_index();
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : done)
+    if (d.first == fn && d.second == dev) return 0;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  done.emplace_back(fn, dev);
+  return 0;
+}
+// Pick the <G, QR> instantiation of a strip kernel template and launch it.
+#define GATE_STRIP_DISPATCH(KERNEL, NV, NS, COEF_FLOATS, ...)                                              \
+  do {                                                                                                      \
+    const int qr_ = strip_qr(g);                                                                            \
+    if (qr_ == 0) return UB2_ERR_SHAPE;                                                                     \
+    const bool g2_ = g.cgs > g.tpp;                                                                         \
+    const size_t coef_ = static_cast<size_t>(COEF_FLOATS) * 4;                                              \
+    int rc_ = 0;                                                                                            \
+    if (!g2_ && qr_ == 4) {                                                                                 \
+      const size_t sm_ = Strip<1, 4, NV, NS>::kBytes + coef_;                                               \
+      rc_ = strip_smem_attr(reinterpret_cast<const void*>(&KERNEL<1, 4>), sm_);                            \
+      if (!rc_) launch(KERNEL<1, 4>, grid, kGateThreads, sm_, s, __VA_ARGS__);                              \
+    } else if (!g2_) {                                                                                      \
+      const size_t sm_ = Strip<1, 8, NV, NS>::kBytes + coef_;                                               \
+      rc_ = strip_smem_attr(reinterpret_cast<const void*>(&KERNEL<1, 8>), sm_);                            \
+      if (!rc_) launch(KERNEL<1, 8>, grid, kGateThreads, sm_, s, __VA_ARGS__);                              \
+    } else if (qr_ == 4) {                                                                                  \
+      const size_t sm_ = Strip<2, 4, NV, NS>::kBytes + coef_;                                               \
+      rc_ = strip_smem_attr(reinterpret_cast<const void*>(&KERNEL<2, 4>), sm_);                            \
+      if (!rc_) launch(KERNEL<2, 4>, grid, kGateThreads, sm_, s, __VA_ARGS__);                              \
+    } else {                                                                                                \
+      const size_t sm_ = Strip<2, 8, NV, NS>::kBytes + coef_;                                               \
+      rc_ = strip_smem_attr(reinterpret_cast<const void*>(&KERNEL<2, 8>), sm_);                            \
+      if (!rc_) launch(KERNEL<2, 8>, grid, kGateThreads, sm_, s, __VA_ARGS__);                              \
+    }                                                                                                       \
+    if (rc_) return rc_;                                                                                    \
+  } while (0)
 
 }  // namespace ub2
 
@@ -539,10 +711,8 @@ int ub2_gate_upstats(const void* q, int ld_q, int N, int hin, int win, int H, in
   if (rc) return rc;
   const int grid = gate_strip_grid(g);
   if (grid != rows) return UB2_ERR_WORKSPACE;
-  if (g.cgs > g.tpp)
-    launch(gate_upstats_kernel<2>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(q), ld_q, partials, g);
-  else
-    launch(gate_upstats_kernel<1>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(q), ld_q, partials, g);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GATE_STRIP_DISPATCH(gate_upstats_kernel, 0, 0, 0, static_cast<cbf>(q), ld_q, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -555,10 +725,9 @@ int ub2_gate_psi(const void* q, int ld_q, const void* xp, int ld_xp, const float
   if (rc) return rc;
   const int grid = gate_strip_grid(g);
   if (partials != nullptr && grid != rows) return UB2_ERR_WORKSPACE;
-  if (g.cgs > g.tpp)
-    launch(gate_psi_kernel<2>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi, psi_raw, partials, g);
-  else
-    launch(gate_psi_kernel<1>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi, psi_raw, partials, g);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GATE_STRIP_DISPATCH(gate_psi_kernel, 1, 0, 4 * Ci, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g,
+                      scale_x, shift_x, wpsi, psi_raw, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -596,10 +765,9 @@ int ub2_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_p
   if (rc) return rc;
   const int grid = gate_strip_grid(g);
   if (grid != rows) return UB2_ERR_WORKSPACE;
-  if (g.cgs > g.tpp)
-    launch(gate_bwd_s_kernel<2>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
-  else
-    launch(gate_bwd_s_kernel<1>, grid, kGateThreads, 0, static_cast<cudaStream_t>(stream), dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GATE_STRIP_DISPATCH(gate_bwd_s_kernel, 1, 2, 4 * Ci, dpsin, psi_raw, coef_psi, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp),
+                      ld_xp, scale_g, shift_g, scale_x, shift_x, wpsi, static_cast<bf>(ds), ld_ds, partials, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -621,10 +789,8 @@ int ub2_gate_bwd_xg(const void* ds, int ld_ds, const void* xp, int ld_xp, const 
   if (rc) return rc;
   const int grid = gate_strip_grid(g);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (g.cgs > g.tpp)
-    launch(gate_bwd_xg_kernel<2>, grid, kGateThreads, 0, s, static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp, static_cast<cbf>(q), ld_q, coef, static_cast<bf>(dxp), ld_dxp, static_cast<bf>(dgup), ld_dg, g);
-  else
-    launch(gate_bwd_xg_kernel<1>, grid, kGateThreads, 0, s, static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp, static_cast<cbf>(q), ld_q, coef, static_cast<bf>(dxp), ld_dxp, static_cast<bf>(dgup), ld_dg, g);
+  GATE_STRIP_DISPATCH(gate_bwd_xg_kernel, 2, 0, 6 * Ci, static_cast<cbf>(ds), ld_ds, static_cast<cbf>(xp), ld_xp, static_cast<cbf>(q),
+                      ld_q, coef, static_cast<bf>(dxp), ld_dxp, static_cast<bf>(dgup), ld_dg, g);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -529,6 +529,51 @@ def predict_mask(logits, threshold=0.5, mask=None, positives=None):
     return mask, positives
 
 
+# --------------------------------------------------------------------------- ConvTranspose2d(k = 2, s = 2)
+def pack_convt_weight(w, bias):
+    """(Cin, Cout, 2, 2) fp32 -> (fwd pack (4*Cout, 1, Cin), dgrad pack (Cin, 1, 4*Cout), scale4, shift4)."""
+    cin, cout = w.shape[0], w.shape[1]
+    assert w.dtype == F32 and w.is_contiguous() and w.shape[2:] == (2, 2)
+    fwd = torch.empty((4 * cout, 1, cin), device=w.device, dtype=BF16)
+    dg = torch.empty((cin, 1, 4 * cout), device=w.device, dtype=BF16)
+    ss = torch.empty((2, 4 * cout), device=w.device, dtype=F32)
+    _C.call("ub2_pack_convt_weight", ptr(w), ptr(bias), ptr(fwd), ptr(dg), ptr(ss[0]), ptr(ss[1]), cin, cout, stream())
+    return fwd, dg, ss[0], ss[1]
+
+
+def shuffle2x2(t, cout, ho, wo):
+    """t (N,h,w,4*Cout) -> (N,ho,wo,Cout): pixel shuffle of the transposed convolution + F.pad (zeros)."""
+    n, h, w, c4, ld = _nhwc(t)
+    assert c4 == 4 * cout
+    out = empty_nhwc(n, ho, wo, cout, t.device)
+    _C.call("ub2_shuffle2x2_fwd", ptr(t), ld, ptr(out), cout, n, h, w, cout, ho, wo, stream(), work=(0.0, _nbytes(t, out)))
+    return out
+
+
+def shuffle2x2_bwd(dout, h, w, dbias=None, want_bias=True):
+    """Transpose of shuffle2x2: (N,ho,wo,Cout) -> dt (N,h,w,4*Cout); the bias gradient (sum of the gathered
+    gradient per channel) is accumulated into ``dbias`` (fresh zeros by default)."""
+    n, ho, wo, cout, ld = _nhwc(dout)
+    dt = empty_nhwc(n, h, w, 4 * cout, dout.device)
+    partials = None
+    rows = 0
+    if want_bias:
+        rows = _rows("ub2_shuffle2x2_rows", n, h, w, cout, ho, wo)
+        partials = torch.empty((rows, cout), device=dout.device, dtype=F64)
+        if dbias is None:
+            dbias = torch.zeros((cout,), device=dout.device, dtype=F32)
+    _C.call("ub2_shuffle2x2_bwd", ptr(dout), ld, ptr(dt), 4 * cout, ptr(partials), rows, ptr(dbias if want_bias else None),
+            n, h, w, cout, ho, wo, stream(), work=(0.0, _nbytes(dout, dt)))
+    return dt, (dbias if want_bias else None)
+
+
+def convt_wgrad_reduce(partial, cin, cout, grad, accumulate=False):
+    """grad (Cin,Cout,2,2) fp32 = (or +=) sum over splits of partial (splits, Cin, 4*Cout)."""
+    assert grad.dtype == F32 and grad.is_contiguous() and partial.is_contiguous()
+    _C.call("ub2_convt_wgrad_reduce", ptr(partial), partial.shape[0], cin, cout, ptr(grad), int(accumulate), stream())
+    return grad
+
+
 def resize_planes(x, ho, wo):
     """fp32 (N,C,h,w) -> (N,C,ho,wo), bilinear, align_corners=True (the deep-supervision resize)."""
     assert x.dim() == 4 and x.dtype == F32 and x.is_contiguous()

@@ -460,17 +460,51 @@ class ConvFn(torch.autograd.Function):
         return dx, gw, gb
 
 
+class ConvTranspose2x2(torch.autograd.Function):
+    """nn.ConvTranspose2d(C, C/2, kernel_size=2, stride=2) + F.pad to the skip size (layers.py:81, :98-102,
+    :217-221).  Because kernel == stride the output pixels do not overlap: a 1x1 convolution to 4*Cout
+    channels on the tensor cores (bias in its epilogue) followed by a pixel shuffle; shuffle, padding, its
+    transpose and the bias gradient are kernels of csrc/shuffle.cu — nothing on this path runs in ATen."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_h, out_w):
+        a = to_nhwc(x)
+        n, h, w, cin = a.shape
+        cout = weight.shape[1]
+        wf, wd, scale4, shift4 = K.pack_convt_weight(weight.contiguous(), bias)
+        t = K.conv_fwd(a, wf, 1, scale=scale4, shift=shift4)
+        out = K.shuffle2x2(t, cout, out_h, out_w)
+        ctx.save_for_backward(a, wd)
+        ctx.geom = (h, w, cin, cout, bias is not None)
+        ctx.params = (weight, bias)
+        return from_nhwc(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, wd = ctx.saved_tensors
+        h, w, cin, cout, has_bias = ctx.geom
+        p_w, p_b = ctx.params
+        need_w = ctx.needs_input_grad[1]
+        need_b = has_bias and ctx.needs_input_grad[2]
+        direct = _grad_targets(*([p_w] + ([p_b] if has_bias else []))) if need_w and (need_b or not has_bias) else None
+        d = to_nhwc(dout)
+        dt, gb = K.shuffle2x2_bwd(d, h, w, dbias=direct[1] if (direct is not None and has_bias) else None, want_bias=need_b)
+        gw = None
+        if need_w:
+            part = K.conv_wgrad(a, dt, 1)
+            if direct is not None:
+                K.convt_wgrad_reduce(part, cin, cout, direct[0], accumulate=True)
+            else:
+                gw = torch.empty((cin, cout, 2, 2), device=d.device, dtype=torch.float32)
+                K.convt_wgrad_reduce(part, cin, cout, gw)
+        dx = from_nhwc(K.conv_fwd(dt, wd, 1)) if ctx.needs_input_grad[0] else None
+        if direct is not None:
+            _grads_done(*([p_w] + ([p_b] if has_bias else [])))
+            return dx, None, None, None, None
+        return dx, gw, gb, None, None
+
+
 def conv_transpose2x2(x, weight, bias, out_h, out_w):
-    """nn.ConvTranspose2d(C, C/2, kernel_size=2, stride=2) + F.pad to the skip size
-    (layers.py:81, :98-102).  Because kernel == stride the output pixels do not overlap: it is a
-    1x1 convolution to 4*Cout channels (on the tensor cores) followed by a pixel shuffle."""
-    cin, cout = weight.shape[0], weight.shape[1]
-    n, _, h, w = x.shape
-    w1 = weight.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)      # row = (i, j, co)
-    y = ConvFn.apply(x, w1, bias.repeat(4))                            # (N, 4*Cout, h, w) channels_last
-    y = y.permute(0, 2, 3, 1).reshape(n, h, w, 2, 2, cout)
-    y = y.permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * h, 2 * w, cout).permute(0, 3, 1, 2)
-    dy, dx = out_h - 2 * h, out_w - 2 * w
-    if dy or dx:
-        y = torch.nn.functional.pad(y, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
-    return y.contiguous(memory_format=torch.channels_last)
+    if not x.is_cuda:
+        raise RuntimeError("unet-b200 modules run on CUDA tensors only (no CPU fallback)")
+    return ConvTranspose2x2.apply(x, weight, bias, int(out_h), int(out_w))
