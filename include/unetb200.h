@@ -252,10 +252,12 @@ int ub2_confusion(const void* pred, const long long* target, int mode, int N, in
  * (element strides), BatchNorm folded with the running statistics, the 3x3 / 1x1 convolutions on
  * the tensor cores as kind::tf32.  Forward only. */
 /* nn.Conv2d (+ folded BN + ReLU) of layers.py:32-37,152,158: in0/in1 fp32 NHWC (virtual concat),
- * wgt = ub2_f32_pack_weight output (Cout,taps,C0+C1) fp32, out fp32 NHWC; out = relu?(scale*acc+shift). */
+ * wgt = ub2_f32_pack_weight output (Cout,taps,C0+C1) fp32, out fp32 NHWC; out = relu?(scale*acc+shift).
+ * exact_out = 0: the result is rounded to TF32 (it feeds the next single-pass convolution: inference);
+ * exact_out = 1: the fp32 accumulator is stored as is (the 3xTF32 launches of the training mode). */
 int ub2_conv_fwd_tf32(const float* in0, int ld_in0, int C0, const float* in1, int ld_in1, int C1,
                       const float* wgt, float* out, int ld_out, int N, int H, int W, int Cout, int taps,
-                      const float* scale, const float* shift, int relu, void* stream);
+                      const float* scale, const float* shift, int relu, int exact_out, void* stream);
 int ub2_f32_pack_weight(const float* w, float* out, int Cout, int Cin, int taps, void* stream);
 /* first conv + folded BN + ReLU: x fp32 NCHW -> out fp32 NHWC (layers.py:32-34, Cin = n_channels) */
 int ub2_f32_conv_in(const float* x, const float* w, const float* scale, const float* shift, float* out, int N,
@@ -312,6 +314,38 @@ int ub2_prepare_batch(const unsigned char* images, const unsigned char* labels, 
  * number of mask pixels set (zeroed by the call).  No resize: the caller's slices are model-sized. */
 int ub2_predict_mask(const float* logits, int N, int C, long long HW, float threshold, unsigned char* mask,
                      int* positives, void* stream);
+
+
+/* ======================= fp32 / TF32 training mode ======================================= */
+/* Activations and gradients are fp32 NHWC (channel stride `ld` where given, else dense), C % 4 == 0.  Forward and
+ * data-gradient convolutions: ONE ub2_conv_fwd_tf32 launch over the 3xTF32 K axis [a_hi | a_lo | a_hi] x [w_hi | w_hi |
+ * w_lo] (ub2_f32_split_tf32, ub2_f32_pack_weight3); weight gradient: ub2_conv_wgrad on the (hi, lo) bf16 halves of
+ * ub2_f32_split_bf16 (kind::tf32 has no MN-major operand mode).  Reductions write one fp64 row per block
+ * (`rows` = the matching *_rows query) that the bf16 path's finalize entry points fold (ub2_bn_finalize,
+ * ub2_bn_bwd_finalize, ub2_gate_bwd_finalize).  See csrc/fp32_train.cu for the per-kernel reference lines. */
+int ub2_f32_channel_rows(long long pixels, int C);
+int ub2_f32_channel_stats(const float* x, int ld, long long pixels, int C, double* partials, int rows, void* stream);
+int ub2_f32_scalar_rows(long long n);
+int ub2_f32_scalar_stats(const float* x, long long n, double* partials, int rows, void* stream);
+int ub2_f32_affine_act(const float* y, const float* scale, const float* shift, float* out, long long pixels, int C, int relu, void* stream);
+int ub2_f32_maxpool_idx(const float* a, float* p, unsigned char* idx, int N, int H, int W, int C, void* stream);
+int ub2_f32_act_bwd_reduce(const float* dA, int ld_da, const float* dP, const unsigned char* idx, const float* y, const float* scale, const float* shift, double* partials, int rows, int N, int H, int W, int C, int relu, void* stream);
+int ub2_f32_act_bwd_apply(const float* dA, int ld_da, const float* dP, const unsigned char* idx, const float* y, const float* scale, const float* shift, const float* coef, float* dy, int N, int H, int W, int C, int relu, void* stream);
+int ub2_f32_upsample_bwd(const float* dout, int ld_dout, float* din, int N, int hin, int win, int hu, int wu, int Ho, int Wo, int C, void* stream);
+int ub2_f32_gate_psi(const float* u, const float* xp, const float* sg, const float* hg, const float* sx, const float* hx, const float* wpsi, float* psi_raw, long long pixels, int Ci, void* stream);
+int ub2_f32_gate_apply(const float* psi_raw, const float* spsi, const float* hpsi, const float* x, float* out, float* a_out, long long pixels, int Cx, void* stream);
+int ub2_f32_gate_rows(long long pixels);
+int ub2_f32_gate_bwd_a(const float* dout, int ld_do, const float* x, const float* a, const float* psi_raw, float* dx, float* dpsin, double* partials, int rows, long long pixels, int Cx, void* stream);
+int ub2_f32_gate_bwd_s(const float* dpsin, const float* psi_raw, const float* coef_psi, const float* u, const float* xp, const float* sg, const float* hg, const float* sx, const float* hx, const float* wpsi, float* ds, double* partials, int rows, long long pixels, int Ci, void* stream);
+int ub2_f32_gate_bwd_xg(const float* ds, const float* xp, const float* u, const float* coef, float* dxp, float* du, long long pixels, int Ci, void* stream);
+int ub2_f32_outc_rows(int N, int H, int W);
+int ub2_f32_outc_bwd(const float* dlogits, const float* a, const float* w, float* da, double* partials, int rows, float* dw, float* db, int N, int H, int W, int C, int K, void* stream);
+int ub2_f32_conv_in_raw(const float* x, const float* w, float* out, int N, int Cin, int H, int W, int Cout, void* stream);
+int ub2_f32_conv_in_wgrad(const float* x, const float* dy, double* partials, int rows, float* grad, int N, int Cin, int H, int W, int Cout, void* stream);
+int ub2_f32_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream);
+int ub2_f32_split_tf32(const float* x0, int ld0, int C0, const float* x1, int ld1, int C1, float* out, long long pixels, void* stream);
+int ub2_f32_pack_weight3(const float* w, float* out, int Cout, int Cin, int taps, int dgrad, void* stream);
+int ub2_f32_upsample_fwd(const float* in, float* out, int N, int hin, int win, int hu, int wu, int Ho, int Wo, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,13 +23,13 @@ int ub2_conv_fwd(const void* in0, int ld_in0, int C0, const void* in1, int ld_in
 
 int ub2_conv_fwd_tf32(const float* in0, int ld_in0, int C0, const float* in1, int ld_in1, int C1,
                       const float* wgt, float* out, int ld_out, int N, int H, int W, int Cout, int taps,
-                      const float* scale, const float* shift, int relu, void* stream) {
+                      const float* scale, const float* shift, int relu, int exact_out, void* stream) {
   ConvFwdArgs a{};
   a.in0 = in0; a.in1 = in1; a.wgt = wgt; a.out0 = out;
   a.scale = scale; a.shift = shift; a.relu = relu;
   a.N = N; a.H = H; a.W = W; a.C0 = C0; a.C1 = C1; a.Cout = Cout; a.taps = taps;
   a.ld_in0 = ld_in0; a.ld_in1 = ld_in1; a.ld0 = ld_out;
-  a.tf32 = 1;
+  a.tf32 = exact_out ? 2 : 1;
   return conv_fwd_launch(a, static_cast<cudaStream_t>(stream));
 }
 

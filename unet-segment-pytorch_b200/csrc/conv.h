@@ -31,7 +31,8 @@ struct ConvFwdArgs {
   int accumulate, relu;
   int stats_rows;
   int bn_override, grid_override;  // tuning / tests; 0 = automatic
-  int tf32;  // fp32 NHWC activations, fp32 (Cout,taps,Cin) weights, fp32 output: kind::tf32 (eval only)
+  int tf32;  // fp32 NHWC activations, fp32 (Cout,taps,Cin) weights, fp32 output: kind::tf32; 1 = output rounded to
+             // TF32 (it feeds the next single-pass convolution: eval), 2 = output kept fp32 (3xTF32 training)
 };
 
 struct ConvFwdParams {

@@ -82,10 +82,14 @@ __device__ __forceinline__ void epi_chunk(const ConvFwdParams& p, uint32_t taddr
     for (int g = 0; g < 8; ++g) {
       if (valid && cbase + g * 4 < p.Cout && cbase + g * 4 < n_hi) {
         float4 o;
-        o.x = tf32_round(v[g * 4 + 0]);
-        o.y = tf32_round(v[g * 4 + 1]);
-        o.z = tf32_round(v[g * 4 + 2]);
-        o.w = tf32_round(v[g * 4 + 3]);
+        if (p.tf32 == 2) {   // training (3xTF32): the accumulator is fp32-accurate, keep it
+          o.x = v[g * 4 + 0]; o.y = v[g * 4 + 1]; o.z = v[g * 4 + 2]; o.w = v[g * 4 + 3];
+        } else {
+          o.x = tf32_round(v[g * 4 + 0]);
+          o.y = tf32_round(v[g * 4 + 1]);
+          o.z = tf32_round(v[g * 4 + 2]);
+          o.w = tf32_round(v[g * 4 + 3]);
+        }
         *reinterpret_cast<float4*>(dstf + g * 4) = o;
       }
     }

@@ -50,6 +50,18 @@ def _nhwc(t: torch.Tensor):
     return n, h, w, c, ld
 
 
+def _nhwc32(t: torch.Tensor):
+    """fp32 / TF32 mode: (N,H,W,C) fp32 whose channel stride may exceed C (a channel slice)."""
+    assert t.dim() == 4 and t.dtype == F32 and t.stride(3) == 1, "expected NHWC fp32"
+    n, h, w, c = t.shape
+    ld = t.stride(2) if w > 1 else c
+    if h > 1:
+        assert t.stride(1) == w * ld, "expected dense NHWC rows"
+    if n > 1:
+        assert t.stride(0) == h * w * ld, "expected dense NHWC images"
+    return n, h, w, c, ld
+
+
 def empty_nhwc(n, h, w, c, device):
     return torch.empty((n, h, w, c), device=device, dtype=BF16)
 

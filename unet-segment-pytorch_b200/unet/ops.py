@@ -427,39 +427,6 @@ class MaxPool2x2(torch.autograd.Function):
         return from_nhwc(K.maxpool_bwd(to_nhwc(dp), pidx, a))
 
 
-class ConvFn(torch.autograd.Function):
-    """Plain convolution (no BN): weight is any (Cout, Cin, k, k) fp32 tensor, k in {1, 3};
-    optional per-output-channel bias added to the fp32 accumulator in the epilogue."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias):
-        a = to_nhwc(x)
-        weight = weight.contiguous()
-        taps = weight.shape[2] * weight.shape[3]
-        wf, wd = K.pack_conv_weight(weight, True, ctx.needs_input_grad[0])
-        ctx.save_for_backward(a, wd)
-        ctx.meta = weight.shape
-        if bias is None:
-            return from_nhwc(K.conv_fwd(a, wf, taps))
-        bias = bias.contiguous().float()
-        return from_nhwc(K.conv_fwd(a, wf, taps, scale=torch.ones_like(bias), shift=bias))
-
-    @staticmethod
-    def backward(ctx, dy):
-        a, wd = ctx.saved_tensors
-        cout, cin, kh, kw = ctx.meta
-        taps = kh * kw
-        d = to_nhwc(dy)
-        gw = gb = None
-        if ctx.needs_input_grad[1]:
-            gw = torch.empty(ctx.meta, device=d.device, dtype=torch.float32)
-            K.wgrad_reduce(K.conv_wgrad(a, d, taps), cout, cin, taps, gw)
-        if ctx.needs_input_grad[2]:
-            gb = d.float().sum(dim=(0, 1, 2))
-        dx = from_nhwc(K.conv_fwd(d, wd, taps)) if ctx.needs_input_grad[0] else None
-        return dx, gw, gb
-
-
 class ConvTranspose2x2(torch.autograd.Function):
     """nn.ConvTranspose2d(C, C/2, kernel_size=2, stride=2) + F.pad to the skip size (layers.py:81, :98-102,
     :217-221).  Because kernel == stride the output pixels do not overlap: a 1x1 convolution to 4*Cout
