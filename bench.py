@@ -476,6 +476,24 @@ def run_ours(args):
         sustained = {"value": B * world * n_sus / (ms_sus * 1e-3), "unit": "images/s", "steps": n_sus,
                      "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus, "clocks": c2}
 
+    # what the collective costs: the same replayed step with the all-reduce left out (measurement knob of the trainer)
+    collective = None
+    if world > 1 and not args.no_extras:
+        os.environ["UB2_SKIP_ALLREDUCE"] = "1"
+        try:
+            t2 = make_trainer(True, not args.no_graph)
+            for _ in range(warm + (4 if not args.no_graph else 0)):
+                t2.step(x_dev, t_dev)
+            ms_nc = timed(lambda: t2.step(x_dev, t_dev), args.steps)
+            collective = {"ms_per_step_without_allreduce": ms_nc / args.steps, "exposed_ms_per_step": (ms - ms_nc) / args.steps,
+                          "bytes_per_step": sum(b.flat.numel() * 4 for b in trainer.buckets), "buckets": len(trainer.buckets),
+                          "what": "same step, same graph capture, gradient all-reduce skipped (replicas diverge: timing only)"}
+            t2.release_graphs()
+            del t2
+        finally:
+            os.environ.pop("UB2_SKIP_ALLREDUCE", None)
+        torch.cuda.empty_cache()
+
     dp_check = None
     if world > 1:
         flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
@@ -548,7 +566,7 @@ def run_ours(args):
         "roofline_wgrad": roofline_wgrad, "roofline_convs": roofline_convs,
         "step_tensor_frac": {"achieved_tflops": step_tflops, "frac_of_burst": step_tflops / float(peaks.get("bf16_tflops", 1640.0)),
                              "what": "training FLOPs of the whole step (SURVEY §8d) / step time: end-to-end tensor-pipe fraction"},
-        "kernels": kernels, "sustained": sustained, "dp_check": dp_check,
+        "kernels": kernels, "sustained": sustained, "dp_check": dp_check, "collective": collective,
     }
 
     # ---------------------------------------------------------------- the other BASELINE configs (N = 1)
@@ -607,6 +625,45 @@ def other_configs(dev, timed, profile_eager, make_trainer, roofline_peak, Infere
             out[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats()
+    # configs[0] and the fp32 accuracy mode: fp32 activations; inference = single-pass TF32 with BN folded, training =
+    # 3xTF32 forward / data gradient + bf16x3 weight gradient (unet/fp32.py)
+    try:
+        import unet
+        unet.set_precision("tf32")
+        torch.manual_seed(42)
+        model = AttentionUNet(1, 2, True, 64).to(dev).eval()
+        x1, _ = synthetic_batch(1, H, W, seed=1234)
+        x1 = x1.to(dev)
+
+        def fwd():
+            with torch.no_grad():
+                model(x1)
+
+        for _ in range(3):
+            fwd()
+        ms = timed(fwd, 20) / 20
+        out["cfg1_attention_fp32_forward_batch1"] = {
+            "workload": "AttentionUNet(1,2) eval forward, 1x1x512x512, fp32 activations / TF32 tensor-core convolutions "
+                        "(BASELINE configs[0]); logits within 1e-3 of the fp32 reference (tests/test_fp32_mode_gpu.py)",
+            "value": 1e3 / ms, "unit": "images/s", "ms": ms, "tflops": FLOPS_FWD["attention"] / ms / 1e9}
+        tr = make_trainer(True, False)
+        x, t = synthetic_batch(4, H, W, seed=1234)
+        x, t = x.to(dev), t.to(dev)
+        for _ in range(2):
+            tr.step(x, t)
+        ms = timed(lambda: tr.step(x, t), 3) / 3
+        out["fp32_mode_train_batch4"] = {
+            "workload": "AttentionUNet train step, batch 4, fp32 accuracy mode (3xTF32 forward / data gradient, bf16x3 weight "
+                        "gradient, fp32 everything else; gradients within 1e-3 per module: tests/test_fp32_train_gpu.py), eager",
+            "value": 4e3 / ms, "unit": "images/s", "ms_per_step": ms}
+        del tr, model, x, t
+    except Exception as e:  # noqa: BLE001
+        out["fp32_mode"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    finally:
+        import unet
+        unet.set_precision("bf16")
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
     # configs[4]: inference, BN folded, fused threshold + confusion counts, batch sweep
     try:
         torch.manual_seed(42)

@@ -131,3 +131,68 @@ def test_dropin_launcher_runs_the_reference_scripts():
         r = subprocess.run([sys.executable, "-m", "unet.dropin", os.path.join(CHECKOUT, "scripts", script), "--help"],
                            capture_output=True, text=True, env=dict(os.environ, PYTHONPATH=PKG), cwd="/tmp")
         assert r.returncode == 0 and "usage:" in r.stdout, r.stdout + r.stderr
+
+
+# --------------------------------------------------------------------------- the scripts themselves, on the GPU
+def _tiny_dataset(root, volumes=5, slices=4, size=64):
+    """PNG slices in the layout LungTumorDataset expects (unet/data/dataset.py:24-34): images/ and labels/,
+    <volume>_slice_<k>.png, 8-bit grey, label 255 inside a disc."""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    for sub in ("images", "labels"):
+        os.makedirs(os.path.join(root, sub), exist_ok=True)
+    yy, xx = np.mgrid[:size, :size]
+    for v in range(volumes):
+        for k in range(slices):
+            img = (rng.normal(110, 40, (size, size))).clip(0, 255).astype(np.uint8)
+            cy, cx, r = rng.integers(16, size - 16, 2).tolist() + [int(rng.integers(4, 9))]
+            lab = (((yy - cy) ** 2 + (xx - cx) ** 2) <= r * r).astype(np.uint8) * 255
+            img[lab > 0] = np.minimum(255, img[lab > 0].astype(int) + 60).astype(np.uint8)
+            name = f"{v}_slice_{k:04d}.png"
+            Image.fromarray(img).save(os.path.join(root, "images", name))
+            Image.fromarray(lab).save(os.path.join(root, "labels", name))
+
+
+@pytest.mark.gpu
+@needs_checkout
+def test_reference_train_and_predict_scripts_run_on_the_b200_package(tmp_path):
+    """The reference's own scripts/train.py and scripts/predict.py, unmodified, through ``python -m unet.dropin``:
+    one epoch on a tiny PNG dataset (dataset, transforms, config, callbacks, checkpoint I/O from the reference's
+    files; model, loss, metrics, EMA from this package, on CUDA), then prediction from the checkpoint it wrote."""
+    import torch
+    import yaml
+    data = tmp_path / "dataset"
+    _tiny_dataset(str(data))
+    with open(os.path.join(CHECKOUT, "configs", "lung_tumor.yaml")) as f:
+        cfg = yaml.safe_load(f)
+    cfg["model"].update(base_features=32)
+    cfg["data"].update(root=str(data), img_size=64, batch_size=2, num_workers=0)
+    cfg["train"].update(epochs=2, accumulation_steps=2)
+    cfg["scheduler"].update(warmup_epochs=1)
+    cfg["ema"] = {"enabled": True, "decay": 0.9}
+    cfg["augmentation"]["enabled"] = False
+    cfg["output"].update(save_dir=str(tmp_path / "runs"), experiment_name="dropin")
+    cfg["device"] = "cuda"
+    cfg_path = tmp_path / "cfg.yaml"
+    cfg_path.write_text(yaml.safe_dump(cfg))
+    env = dict(os.environ, PYTHONPATH=PKG)
+    r = subprocess.run([sys.executable, "-m", "unet.dropin", os.path.join(CHECKOUT, "scripts", "train.py"), "--config", str(cfg_path)],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
+    weights = [os.path.join(dp, f) for dp, _, fs in os.walk(tmp_path / "runs") for f in fs if f.endswith(".pt")]
+    assert any(w.endswith("last.pt") for w in weights), weights
+    ckpt = torch.load([w for w in weights if w.endswith("last.pt")][0], map_location="cpu", weights_only=False)
+    sys.path.insert(0, PKG)
+    from unet.models import AttentionUNet
+    model = AttentionUNet(1, 2, True, 32)
+    model.load_state_dict(ckpt["model_state_dict"], strict=True)
+    assert all(torch.isfinite(v).all() for v in ckpt["model_state_dict"].values() if v.is_floating_point())
+    out = tmp_path / "pred"
+    img = sorted(os.listdir(data / "images"))[0]
+    r = subprocess.run([sys.executable, "-m", "unet.dropin", os.path.join(CHECKOUT, "scripts", "predict.py"), "--weights",
+                        [w for w in weights if w.endswith("last.pt")][0], "--source", str(data / "images" / img), "--output",
+                        str(out), "--img-size", "64", "--device", "cuda"],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0, (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
+    assert any(f.endswith(".png") for _, _, fs in os.walk(out) for f in fs)

@@ -82,6 +82,14 @@ class BatchShardedTrainer:
         self._first = self._last = True   # phase of the micro-batch being run (set by step)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        # measurement knobs (bench.py's collective-exposure figures; never set in production):
+        #   UB2_SKIP_ALLREDUCE=1   run the multi-rank step WITHOUT its collectives (replicas then diverge)
+        #   UB2_ALLREDUCE_AT_END=1 launch every bucket's all-reduce after backward instead of as it fills
+        #   UB2_BUCKET_MB=<float>  bucket size override
+        import os
+        self._skip_collectives = os.environ.get("UB2_SKIP_ALLREDUCE", "0") == "1"
+        self._collectives_at_end = os.environ.get("UB2_ALLREDUCE_AT_END", "0") == "1"
+        bucket_mb = float(os.environ.get("UB2_BUCKET_MB", bucket_mb))
         self.buffer_sync = buffer_sync
         self._buffers_dirty = False
         if self.world > 1:
@@ -165,7 +173,8 @@ class BatchShardedTrainer:
             items, bucket.deferred = bucket.deferred, []
             wgrad_reduce_multi(items, accumulate=True)
             bucket.pending -= len(items)
-        if bucket.pending == 0 and self.world > 1 and self._last and bucket.work is None:
+        if (bucket.pending == 0 and self.world > 1 and self._last and bucket.work is None
+                and not self._skip_collectives and not self._collectives_at_end):
             bucket.work = dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _defer_reduce(self, param, item) -> None:
@@ -240,9 +249,9 @@ class BatchShardedTrainer:
     def _optimizer_tail(self) -> None:
         """All-reduce what is not in flight yet, wait, clip + optimizer step, EMA (train.py:139-147)."""
         self._buffers_dirty = True
-        if self.world > 1:
+        if self.world > 1 and not self._skip_collectives:
             for b in self.buckets:
-                if b.work is None:  # a parameter without gradient this step
+                if b.work is None:  # a parameter without gradient this step (or UB2_ALLREDUCE_AT_END)
                     b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             for b in self.buckets:
                 b.work.wait()
