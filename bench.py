@@ -362,6 +362,30 @@ def kernel_table(prof, steps, peaks, tensor_peak):
     return table
 
 
+def replica_check(model, trainer, dev, world):
+    """Every rank's parameters against rank 0's (broadcast), per parameter: replicas must be bit-identical."""
+    import torch
+    import torch.distributed as dist
+
+    names, worst = [], 0.0
+    for name, p in model.named_parameters():
+        ref = p.detach().clone()
+        dist.broadcast(ref, src=0)
+        d = (p.detach() - ref).abs().max().reshape(1)
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        if d.item() != 0.0:
+            names.append((name, d.item()))
+            worst = max(worst, d.item())
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    sums = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(sums, flat.double().sum().reshape(1))
+    return {"max_abs_param_diff_vs_rank0": worst, "param_checksums_equal": len({s.item() for s in sums}) == 1,
+            "params_that_differ": len(names), "first_differing": names[:6], "param_checksum": sums[0].item(),
+            "optimizer_steps": trainer._steps,
+            "what": "after the timed steps every rank's parameters are compared with rank 0's (broadcast) and the "
+                    "per-rank fp64 checksums gathered: replicas must be bit-identical"}
+
+
 def run_ours(args):
     for p in (PKG, ROOT):
         if p not in sys.path:
@@ -435,6 +459,7 @@ def run_ours(args):
         sampler.start()
     ms = timed(lambda: trainer.step(x_dev, t_dev), args.steps)
     clocks = sampler.stop() if sampler else None
+    dp_check_after_graph = replica_check(model, trainer, dev, world) if world > 1 else None
 
     def profile_eager(tr, x, t, steps):
         """Per-launch CUDA events (and the launch count) in an eager pass of the very same step — a
@@ -496,17 +521,7 @@ def run_ours(args):
 
     dp_check = None
     if world > 1:
-        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
-        ref = flat.clone()
-        dist.broadcast(ref, src=0)
-        diff = (flat - ref).abs().max().reshape(1)
-        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
-        sums = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
-        dist.all_gather(sums, flat.double().sum().reshape(1))
-        dp_check = {"max_abs_param_diff_vs_rank0": diff.item(), "param_checksums_equal": len({s.item() for s in sums}) == 1,
-                    "param_checksum": sums[0].item(), "optimizer_steps": trainer._steps,
-                    "what": "after the timed steps every rank's parameters are compared with rank 0's (broadcast) "
-                            "and the per-rank fp64 checksums gathered: replicas must be bit-identical"}
+        dp_check = replica_check(model, trainer, dev, world)
 
     if rank != 0:
         _shutdown(trainer, world)
@@ -566,7 +581,8 @@ def run_ours(args):
         "roofline_wgrad": roofline_wgrad, "roofline_convs": roofline_convs,
         "step_tensor_frac": {"achieved_tflops": step_tflops, "frac_of_burst": step_tflops / float(peaks.get("bf16_tflops", 1640.0)),
                              "what": "training FLOPs of the whole step (SURVEY §8d) / step time: end-to-end tensor-pipe fraction"},
-        "kernels": kernels, "sustained": sustained, "dp_check": dp_check, "collective": collective,
+        "kernels": kernels, "sustained": sustained, "dp_check": dp_check, "dp_check_after_graph_steps": dp_check_after_graph,
+        "collective": collective,
     }
 
     # ---------------------------------------------------------------- the other BASELINE configs (N = 1)

@@ -184,3 +184,87 @@ def test_flush_applies_the_left_over_micro_batches():
     (crit(ref(x), t) / 3).backward()
     for a, b in zip(model.parameters(), ref.parameters()):
         assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-7)
+
+
+# --------------------------------------------------------------------------- gradient sink + hooks, two ranks
+class _SinkLinear(torch.autograd.Function):
+    """What unet.ops does on the GPU, on CPU tensors: with a gradient sink installed the backward adds the
+    parameter gradient straight into ``param.grad`` (the bucket view), announces it and returns None."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        ctx.param = w
+        return x @ w.t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        from unet import ops
+        x, w = ctx.saved_tensors
+        gw = dy.reshape(-1, dy.shape[-1]).t() @ x.reshape(-1, x.shape[-1])
+        t = ops._grad_targets(ctx.param)
+        if t is not None:
+            t[0].add_(gw)
+            ops._grads_done(ctx.param)
+            gw = None
+        return dy @ w, gw
+
+
+class _SinkNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(0)
+        self.w1 = nn.Parameter(torch.randn(16, 8) * 0.3)
+        self.w2 = nn.Parameter(torch.randn(16, 16) * 0.3)
+        self.w3 = nn.Parameter(torch.randn(4, 16) * 0.3)
+        self.b = nn.Parameter(torch.zeros(4))          # an ordinary autograd gradient next to the sunk ones
+
+    def forward(self, x):
+        h = torch.tanh(_SinkLinear.apply(x, self.w1))
+        h = torch.tanh(_SinkLinear.apply(h, self.w2))
+        return _SinkLinear.apply(h, self.w3) + self.b
+
+
+def _sink_data(rank):
+    g = torch.Generator().manual_seed(50 + rank)
+    return torch.randn(6, 8, generator=g), torch.randint(0, 4, (6,), generator=g)
+
+
+def _sink_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from unet.parallel import BatchShardedTrainer
+    model = _SinkNet()
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    # tiny buckets: w3+b | w2 | w1 — a bucket announced twice would be all-reduced before backward has filled it
+    tr = BatchShardedTrainer(model, nn.CrossEntropyLoss(), opt, grad_clip=0.0, bucket_mb=0.0004)
+    assert len(tr.buckets) >= 2
+    for _ in range(3):
+        tr.step(*_sink_data(rank))
+    for b in tr.buckets:
+        assert b.pending == 0, b.pending          # every gradient counted exactly once
+    torch.save([p.detach().clone() for p in model.parameters()], f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_gradient_sink_with_hooks_counts_each_gradient_once(tmp_path):
+    """Two ranks, kernels that write their gradients through the sink (as every unet.ops function does on the
+    GPU) next to a parameter that goes through autograd: replicas stay bit-identical and equal the reference's
+    accumulation loop.  Round 1 counted sunk gradients twice when world_size > 1 (sink + post-accumulate hook),
+    launched the all-reduce of a bucket before backward had filled it, and the ranks drifted apart."""
+    out = str(tmp_path / "r")
+    mp.spawn(_sink_worker, args=(2, 29617, out), nprocs=2, join=True)
+    r0, r1 = (torch.load(f"{out}.{r}", weights_only=False) for r in range(2))
+    for a, b in zip(r0, r1):
+        assert torch.equal(a, b)
+    ref = _SinkNet()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    crit = nn.CrossEntropyLoss()
+    for _ in range(3):
+        opt.zero_grad()
+        for r in range(2):
+            x, t = _sink_data(r)
+            (crit(ref(x), t) / 2).backward()
+        opt.step()
+    for a, b in zip(r0, ref.parameters()):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)

@@ -27,11 +27,12 @@ from .optim import FusedAdamW
 
 
 class _Bucket:
-    __slots__ = ("flat", "params", "pending", "work", "deferred")
+    __slots__ = ("flat", "params", "pending", "work", "deferred", "seen")
 
     def __init__(self, flat, params):
         self.flat, self.params, self.pending, self.work = flat, params, 0, None
         self.deferred = []   # split-K folds of this bucket's conv weights, launched together
+        self.seen = set()    # parameters already counted this step (a gradient is reported ONCE, see _bucket_ready)
 
 
 class _GradSink:
@@ -165,7 +166,16 @@ class BatchShardedTrainer:
                 if self.world > 1:
                     p.register_post_accumulate_grad_hook(self._make_hook(b))
 
-    def _bucket_ready(self, bucket: _Bucket, n: int = 1) -> None:
+    def _bucket_ready(self, bucket: _Bucket, n: int = 1, param=None) -> None:
+        """``param``'s gradient is complete in the bucket.  A parameter can be announced twice — by the kernel
+        path's gradient sink AND by the post-accumulate hook autograd runs for the same leaf (the engine still
+        visits the AccumulateGrad node of an input whose backward returned None) — and must count once: a
+        bucket whose count reached zero early was all-reduced while half of its gradients were still being
+        written, so every rank kept a different sum (found by bench.py's replica check, round 2)."""
+        if param is not None:
+            if id(param) in bucket.seen:
+                return
+            bucket.seen.add(id(param))
         bucket.pending -= n
         if bucket.deferred and bucket.pending == len(bucket.deferred):
             # every other gradient of the bucket is in: fold all its split-K partials in one go
@@ -183,6 +193,7 @@ class BatchShardedTrainer:
             from .kernels import wgrad_reduce
             wgrad_reduce(*item, accumulate=True)
             return
+        b.seen.add(id(param))     # counted when its fold is launched
         b.deferred.append(item)
         self._bucket_ready(b, 0)
 
@@ -196,14 +207,14 @@ class BatchShardedTrainer:
                 b.pending -= len(items)
 
     def _make_hook(self, bucket: _Bucket):
-        return lambda _param: self._bucket_ready(bucket)
+        return lambda param: self._bucket_ready(bucket, 1, param)
 
     def _grad_sink(self, param) -> None:
         """Called by unet.ops when a kernel has accumulated ``param``'s gradient straight into its
         bucket view (no autograd AccumulateGrad node runs for it, hence no hook)."""
         b = self._bucket_of.get(id(param))
         if b is not None:
-            self._bucket_ready(b)
+            self._bucket_ready(b, 1, param)
 
     # ------------------------------------------------------------------ one optimizer step
     def _forward(self, images: torch.Tensor):
@@ -217,6 +228,7 @@ class BatchShardedTrainer:
             b.pending = len(b.params)
             b.work = None
             b.deferred = []
+            b.seen = set()
         dev = next(self.model.parameters()).device
         if dev.type == "cuda":
             if self._packer is None:
