@@ -17,9 +17,9 @@ opt = FusedAdamW(model.parameters(), lr=0.0, weight_decay=0.0)   # lr 0: paramet
 tr = BatchShardedTrainer(model, DiceBCELoss(), opt, grad_clip=0.0)
 events = []
 orig = tr._bucket_ready
-def traced(bucket, n=1):
+def traced(bucket, n=1, param=None):
     before = bucket.pending
-    orig(bucket, n)
+    orig(bucket, n, param)
     events.append((tr.buckets.index(bucket), before, bucket.pending, len(bucket.deferred), bucket.work is not None))
 tr._bucket_ready = traced
 x, t = synthetic_batch(2, 128, 128, seed=1234 + rank)
