@@ -87,6 +87,9 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C,
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
                  uint32_t bc, uint32_t br, int swizzle_bytes, int elem_bytes = 2);
 int num_sms();
+// Resident CTA pairs a cluster kernel may use: the occupancy figure, capped by the SMs this process may fill
+// (UB2_RESERVE_SMS leaves SMs to co-running kernels of another stream — the NCCL all-reduce of a multi-GPU step).
+inline int cap_clusters(int occupancy_clusters) { const int c = num_sms() / 2; return occupancy_clusters < c ? occupancy_clusters : c; }
 // Which kernel the dispatcher picked for the calling thread's last convolution launch (tests assert it):
 // forward / dgrad 1 = conv_fwd (one CTA, per tap), 2 = conv_fwd2 (CTA pair, per tap), 3 = conv_halo (one CTA,
 // halo resident), 4 = conv_halo2 (CTA pair, halo resident); weight gradient 11..14 likewise.

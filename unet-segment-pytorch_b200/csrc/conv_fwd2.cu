@@ -315,7 +315,8 @@ int conv_fwd2_launch(const ConvFwdArgs& a, cudaStream_t stream) {
   if (rc) return rc;
 
   const int total_items = ((m_tiles + 1) / 2) * p.n_tiles;
-  const int clusters = max_clusters[variant] < total_items ? max_clusters[variant] : total_items;
+  const int resident = cap_clusters(max_clusters[variant]);
+  const int clusters = resident < total_items ? resident : total_items;
   const int grid = 2 * clusters;
   if (a.stats && grid > a.stats_rows) return UB2_ERR_WORKSPACE;
   const size_t smem = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(Fwd2SmemHeader) + stats_bytes;

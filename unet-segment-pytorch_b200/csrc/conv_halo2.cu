@@ -346,7 +346,7 @@ int conv_halo2_launch(const ConvFwdArgs& a, cudaStream_t stream) {
     if (cap_env > 0 && cap_env < n) n = cap_env;
     max_clusters[acc] = n;
   }
-  int clusters = max_clusters[acc];
+  int clusters = cap_clusters(max_clusters[acc]);
   if (verbose) fprintf(stderr, "ub2: conv_halo2 max resident clusters %d, pairs %d, R %d, b_stages %d\n", clusters, pairs, R, b_stages);
   if (clusters > pairs) clusters = pairs;
   const int grid = 2 * clusters;

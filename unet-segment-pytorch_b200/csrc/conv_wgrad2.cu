@@ -302,7 +302,8 @@ int conv_wgrad2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
 
   // split K so that the cluster grid is one full wave of work items, each with >= 4 pixel chunks
   const int tiles = ((m_tiles + 1) / 2) * p.n_tiles;
-  int splits = max_clusters / tiles;
+  const int resident = cap_clusters(max_clusters);
+  int splits = resident / tiles;
   if (splits > total_chunks / 4) splits = total_chunks / 4;
   if (splits < 1) splits = 1;
   if (splits > total_chunks) splits = total_chunks;
@@ -326,7 +327,7 @@ int conv_wgrad2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   if (rc) return rc;
 
   const int total_items = tiles * splits;
-  const int grid = 2 * (max_clusters < total_items ? max_clusters : total_items);
+  const int grid = 2 * (resident < total_items ? resident : total_items);
   const size_t smem = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(Wg2SmemHeader);
   note_variant(12);
   launch(conv_wgrad2_kernel, grid, kW2Threads, smem, stream, tmA0, tmA1, tmDY, p);

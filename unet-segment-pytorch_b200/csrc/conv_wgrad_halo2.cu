@@ -328,7 +328,8 @@ int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     max_clusters = n;
   }
   const int groups = p.tapsplit ? 1 : (p.kchunks / 2) * p.tapgroups;   // cluster work items per split
-  int splits = max_clusters / groups;
+  const int resident = cap_clusters(max_clusters);
+  int splits = resident / groups;
   if (splits < 1) splits = 1;
   if (splits > p.blocks) splits = p.blocks;
   if (splits > a.max_splits) splits = a.max_splits;
@@ -352,7 +353,7 @@ int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   if (rc) return rc;
 
   const int items = groups * splits;
-  const int grid = 2 * (items < max_clusters ? items : max_clusters);
+  const int grid = 2 * (items < resident ? items : resident);
   const size_t smem = 1024 + 2 * static_cast<size_t>(p.a_bytes) + static_cast<size_t>(b_stages) * p.b_stage_bytes +
                       sizeof(WgHalo2Header);
   note_variant(14);

@@ -3,6 +3,7 @@
 // libcuda and still loads on a box without a driver (symbol checks on CPU).
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "conv.h"
@@ -90,6 +91,10 @@ int num_sms() {
       cached = n;
     else
       return 148;
+    // UB2_RESERVE_SMS=k: size every grid for k SMs fewer (persistent kernels then leave room for the NCCL kernels
+    // of an overlapped all-reduce instead of being split into two waves by them)
+    static const int reserve = [] { const char* e = getenv("UB2_RESERVE_SMS"); return e ? atoi(e) : 0; }();
+    if (reserve > 0 && cached - reserve >= 8) cached -= reserve;
   }
   return cached;
 }
