@@ -182,6 +182,13 @@ int ub2_gate_psi(const void* q, int ld_q, const void* xp, int ld_xp, const float
                  float* psi_raw, double* partials, int rows, int N, int hin, int win, int H, int W,
                  int Ci, void* stream);
 /* a = sigmoid(BN_psi(psi_raw)); out = x * a (layers.py:165-166, :192). */
+/* Inference only (BatchNorm frozen, nothing saved): psi, sigmoid and out = x * a in ONE pass over q, xp and x
+ * (north_star (3)); needs Cx == 2 * Ci (layers.py:147-148's default inter-channel count), else UB2_ERR_SHAPE and the
+ * caller runs ub2_gate_psi + ub2_gate_apply. */
+int ub2_gate_fused_eval(const void* q, int ld_q, const void* xp, int ld_xp, const void* x, int ld_x, const float* scale_g,
+                        const float* shift_g, const float* scale_x, const float* shift_x, const float* wpsi,
+                        const float* scale_psi, const float* shift_psi, void* out, int ld_out, int N, int hin, int win,
+                        int H, int W, int Ci, int Cx, void* stream);
 int ub2_gate_apply(const float* psi_raw, const float* scale_psi, const float* shift_psi, const void* x,
                    int ld_x, void* out, int ld_out, float* a_out, int N, int H, int W, int Cx,
                    void* stream);

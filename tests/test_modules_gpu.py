@@ -492,3 +492,68 @@ def test_full_size_step_is_deterministic_and_finite():
     for a, b in zip(g0, g1):
         assert torch.equal(a, b) and torch.isfinite(a).all()
     assert torch.equal(rm0, rm1) and rm0.abs().sum() > 0
+
+
+@pytest.mark.parametrize("n,h,w,ci", [(2, 16, 16, 64), (1, 13, 19, 32), (2, 64, 64, 128), (1, 512, 512, 32)])
+def test_gate_fused_eval_equals_two_passes(n, h, w, ci):
+    """Inference runs psi + sigmoid + gating as ONE kernel (north_star (3)): bit-identical to gate_psi followed by
+    gate_apply, which the training path and its parity tests use."""
+    from unet import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(ci + h)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    hin, win = (h + 1) // 2, (w + 1) // 2
+    q, xp, x = rnd(n, hin, win, ci).bfloat16(), rnd(n, h, w, ci).bfloat16(), rnd(n, h, w, 2 * ci).bfloat16()
+    sg, sx = rnd(ci).abs() + 0.5, rnd(ci).abs() + 0.5
+    hg, hx, wpsi = rnd(ci) * 0.3, rnd(ci) * 0.3, rnd(ci) * 0.2
+    sp, hp = torch.tensor([0.7], device="cuda"), torch.tensor([-0.1], device="cuda")
+    psi, _ = K.gate_psi(q, xp, sg, hg, sx, hx, wpsi, stats=False)
+    ref, _ = K.gate_apply(psi, sp, hp, x, save_a=False)
+    got = K.gate_fused_eval(q, xp, x, sg, hg, sx, hx, wpsi, sp, hp)
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32"])
+def test_base_features_16_gate_with_8_inter_channels(precision):
+    """AttentionUNet(base_features=16): up4's gate has 8 inter-channels (unet/models/unet.py:137-164 accepts any
+    base_features), below the tensor cores' multiple-of-16 granularity — the gate runs through a zero-padded view
+    (models/layers.py:_PaddedGate).  Eval logits vs the oracle, one train step (loss, finite gradients of the right
+    shapes, the gate's BatchNorm running statistics written back), state_dict layout unchanged."""
+    import unet
+    from unet.utils.loss import DiceBCELoss
+    unet.set_precision(precision)
+    try:
+        model, sd, cfg = _build(True, 16, 41)
+        assert model.up4.attention.W_g[0].weight.shape[0] == 8
+        x, t = O.synthetic_batch(2, 64, 64, seed=12, fg_fraction=0.05)
+        model = model.cuda().eval()
+        with torch.no_grad():
+            logits = model(x.cuda())
+        ref = O.unet_forward(x, sd, attention=True, training=False)
+        tol = 2e-2 if precision == "bf16" else 1e-3
+        e = rel_l2(logits, ref)
+        assert e <= tol, f"eval logits rel-L2 {e:.3e}"
+        model.train()
+        out = model(x.cuda())
+        loss = DiceBCELoss()(out, t.cuda())
+        loss.backward()
+        ref_state = O.clone_state(sd)
+        ref_loss, ref_logits, ref_grads = O.train_grads(x, t, ref_state, attention=True)
+        cos = {k: cosine(p.grad, ref_grads[k]) for k, p in model.named_parameters() if p.numel() > 1}
+        record(f"base_features=16 [{precision}]", eval_logits_rel_l2=e, loss=loss.item(), loss_oracle=ref_loss.item(),
+               train_logits_rel_l2=rel_l2(out, ref_logits), grad_cos_min=min(cos.values()),
+               grad_cos_gate8={k: v for k, v in cos.items() if k.startswith("up4.attention")})
+        assert abs(loss.item() - ref_loss.item()) <= (5e-2 if precision == "bf16" else 1e-4) * abs(ref_loss.item())
+        for k, p in model.named_parameters():
+            assert p.grad is not None and p.grad.shape == p.shape and torch.isfinite(p.grad).all(), k
+        gate_cos = [v for k, v in cos.items() if k.startswith("up4.attention")]
+        # bf16 train mode end to end at random init is chaotic for EVERY parameter (test_train_step_end_to_end_report);
+        # the fp32 mode is the discriminating check of the padded gate's arithmetic
+        assert min(gate_cos) >= (0.8 if precision == "bf16" else 0.999), cos
+        got_sd = model.state_dict()
+        assert list(got_sd.keys()) == list(sd.keys())
+        for k in ("up4.attention.W_g.1.running_mean", "up4.attention.W_x.1.running_var"):
+            assert got_sd[k].shape == sd[k].shape
+            assert torch.allclose(got_sd[k].cpu(), ref_state[k], rtol=5e-2, atol=5e-3), k
+        assert int(got_sd["up4.attention.W_g.1.num_batches_tracked"]) == int(sd["up4.attention.W_g.1.num_batches_tracked"]) + 1
+    finally:
+        unet.set_precision("bf16")

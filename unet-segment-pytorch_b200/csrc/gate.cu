@@ -404,6 +404,61 @@ gate_psi_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat
   if (partials != nullptr) block_reduce_scalars<2>(st, partials + static_cast<size_t>(blockIdx.x) * 2, smem);
 }
 
+// Inference (no BatchNorm reduction forces phases): psi, sigmoid and the gating of the skip in ONE pass —
+// north_star (3).  The skip tensor's channels are streamed through the same ring as two more operands
+// (x[:, :Ci] and x[:, Ci:]; the gate's inter-channel count is half the skip's, layers.py:147-148), so the
+// thread group that reduced a pixel's psi also scales and stores that pixel.
+template <int G, int QR>
+__global__ void __launch_bounds__(kGateThreads)
+gate_fused_eval_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat16* __restrict__ xp, int ld_xp,
+                       const __nv_bfloat16* __restrict__ x, int ld_x, const float* __restrict__ sg,
+                       const float* __restrict__ hg, const float* __restrict__ sx, const float* __restrict__ hx,
+                       const float* __restrict__ wpsi, const float* __restrict__ spsi, const float* __restrict__ hpsi,
+                       __nv_bfloat16* __restrict__ out, int ld_out, GateGeom g) {
+  pdl_trigger();
+  pdl_wait();
+  typedef Strip<G, QR, 3, 0> S_t;
+  S_t S;
+  const __nv_bfloat16* const vptr[3] = {xp, x, x + g.C};
+  const int vld[3] = {ld_xp, ld_x, ld_x};
+  const float* const sptr[1] = {nullptr};
+  extern __shared__ __align__(16) uint8_t strip_smem_c[];
+  const GateCoef cf = gate_coef_load(reinterpret_cast<float*>(strip_smem_c + S_t::kBytes), sg, hg, sx, hx, wpsi, g.C);
+  const float ps = __ldg(spsi), ph = __ldg(hpsi);
+  GATE_STRIP_BEGIN(S, g, q, ld_q, vptr, vld, sptr)
+    float dot = 0.f;
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+      if (S.lane_on(g, gi)) {
+        const int cg = S.j + gi * g.tpp;
+        const F8 u = S.up(gi);
+        const F8 xv = S.vec(ho, 0, gi);
+        const F8 vsg = cf.get(0, cg, g.C), vsx = cf.get(1, cg, g.C), vh = cf.get(2, cg, g.C), vw = cf.get(3, cg, g.C);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float t = fmaf(u.v[k], vsg.v[k], fmaf(xv.v[k], vsx.v[k], vh.v[k]));
+          dot = fmaf(vw.v[k], fmaxf(t, 0.f), dot);
+        }
+      }
+    }
+    dot = group_sum(dot, g.tpp);
+    const float a = 1.f / (1.f + __expf(-fmaf(dot, ps, ph)));   // as gate_apply_kernel
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+      if (S.lane_on(g, gi)) {
+        const int cg = S.j + gi * g.tpp;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          F8 v = S.vec(ho, 1 + half, gi);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v.v[k] *= a;
+          store8(out + static_cast<size_t>(pix) * ld_out + half * g.C + cg * 8, v);
+        }
+      }
+    }
+  GATE_STRIP_END
+}
+
 __global__ void __launch_bounds__(256)
 gate_apply_kernel(const float* __restrict__ psi_raw, const float* __restrict__ spsi,
                   const float* __restrict__ hpsi, const __nv_bfloat16* __restrict__ x, int ld_x,
@@ -728,6 +783,22 @@ int ub2_gate_psi(const void* q, int ld_q, const void* xp, int ld_xp, const float
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GATE_STRIP_DISPATCH(gate_psi_kernel, 1, 0, 4 * Ci, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, scale_g, shift_g,
                       scale_x, shift_x, wpsi, psi_raw, partials, g);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int ub2_gate_fused_eval(const void* q, int ld_q, const void* xp, int ld_xp, const void* x, int ld_x, const float* scale_g,
+                        const float* shift_g, const float* scale_x, const float* shift_x, const float* wpsi,
+                        const float* scale_psi, const float* shift_psi, void* out, int ld_out, int N, int hin, int win,
+                        int H, int W, int Ci, int Cx, void* stream) {
+  if (Cx != 2 * Ci) return UB2_ERR_SHAPE;   // the fused pass streams the skip as two Ci-channel halves
+  GateGeom g;
+  int rc = make_gate_geom(&g, N, H, W, Ci, hin, win);
+  if (rc) return rc;
+  if (ld_x % 8 || ld_out % 8 || ld_xp % 8 || ld_q % 8) return UB2_ERR_ALIGN;
+  const int grid = gate_strip_grid(g);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GATE_STRIP_DISPATCH(gate_fused_eval_kernel, 3, 0, 4 * Ci, static_cast<cbf>(q), ld_q, static_cast<cbf>(xp), ld_xp, static_cast<cbf>(x),
+                      ld_x, scale_g, shift_g, scale_x, shift_x, wpsi, scale_psi, shift_psi, static_cast<bf>(out), ld_out, g);
   return static_cast<int>(cudaGetLastError());
 }
 

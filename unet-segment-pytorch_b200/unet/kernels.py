@@ -335,6 +335,17 @@ def gate_psi(q, xp, sg, hg, sx, hx, wpsi, stats=True):
     return psi, partials
 
 
+def gate_fused_eval(q, xp, x, sg, hg, sx, hx, wpsi, spsi, hpsi):
+    """Inference: out = x * sigmoid(BN_psi(w_psi . relu(BN_g(up q) + BN_x(xp)))) in one pass (Cx == 2*Ci)."""
+    n, hin, win, ci, ld_q = _nhwc(q)
+    _, h, w, _, ld_xp = _nhwc(xp)
+    _, _, _, cx, ld_x = _nhwc(x)
+    out = empty_nhwc(n, h, w, cx, x.device)
+    _C.call("ub2_gate_fused_eval", ptr(q), ld_q, ptr(xp), ld_xp, ptr(x), ld_x, ptr(sg), ptr(hg), ptr(sx), ptr(hx), ptr(wpsi),
+            ptr(spsi), ptr(hpsi), ptr(out), cx, n, hin, win, h, w, ci, cx, stream(), work=(0.0, _nbytes(q, xp, x, out)))
+    return out
+
+
 def gate_apply(psi, spsi, hpsi, x, save_a=True):
     n, h, w, cx, ld = _nhwc(x)
     out = empty_nhwc(n, h, w, cx, x.device)

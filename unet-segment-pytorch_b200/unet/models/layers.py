@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import fp32, ops
 
@@ -116,6 +117,55 @@ class OutConv(nn.Module):
         return ops.OutConvFn.apply(x, self.conv.weight, self.conv.bias)
 
 
+class _BnView:
+    """What unet.ops / unet.fp32 read from a BatchNorm2d, with the channel vectors padded by `pad` neutral
+    channels (gamma 1, beta 0, running statistics 0 / 1); ``write_back`` returns the real channels' running
+    statistics to the module (``num_batches_tracked`` is shared and advanced in place)."""
+
+    def __init__(self, bn: nn.BatchNorm2d, pad: int):
+        self._bn, self._c = bn, bn.num_features
+        self.training, self.momentum, self.eps = bn.training, bn.momentum, bn.eps
+        self.track_running_stats = bn.track_running_stats
+        self.weight = F.pad(bn.weight, (0, pad), value=1.0)
+        self.bias = F.pad(bn.bias, (0, pad))
+        self.running_mean = F.pad(bn.running_mean, (0, pad)) if bn.running_mean is not None else None
+        self.running_var = F.pad(bn.running_var, (0, pad), value=1.0) if bn.running_var is not None else None
+        self.num_batches_tracked = bn.num_batches_tracked
+
+    @torch.no_grad()
+    def write_back(self):
+        if self.training and self.track_running_stats and self.running_mean is not None:
+            self._bn.running_mean.copy_(self.running_mean[:self._c])
+            self._bn.running_var.copy_(self.running_var[:self._c])
+
+
+class _W:
+    def __init__(self, weight):
+        self.weight = weight
+
+
+class _PaddedGate:
+    """An AttentionGate whose inter-channel count is not a multiple of 16 (base_features=16: 8 channels), seen
+    through padding: the tensor-core kernels need K and N in multiples of 16, so W_g / W_x get zero output rows,
+    psi zero input columns and the two BatchNorms neutral channels.  The padded channels stay exactly zero through
+    the gate (zero projection -> BatchNorm of a zero channel -> ReLU(0) -> zero psi weight), gradients reach the real
+    parameters through the padding's own autograd, and the module's parameters / state_dict are untouched."""
+
+    def __init__(self, gate: "AttentionGate", pad: int):
+        self._gate = gate
+        self.training = gate.training
+        self.W_g = (_W(F.pad(gate.W_g[0].weight, (0, 0, 0, 0, 0, 0, 0, pad))), _BnView(gate.W_g[1], pad))
+        self.W_x = (_W(F.pad(gate.W_x[0].weight, (0, 0, 0, 0, 0, 0, 0, pad))), _BnView(gate.W_x[1], pad))
+        self.psi = (_W(F.pad(gate.psi[0].weight, (0, 0, 0, 0, 0, pad))), gate.psi[1])
+
+    def parameters(self):
+        return self._gate.parameters()
+
+    def write_back(self):
+        self.W_g[1].write_back()
+        self.W_x[1].write_back()
+
+
 class AttentionGate(nn.Module):
     """Additive attention gate.  Reference: layers.py:126-192."""
 
@@ -131,10 +181,22 @@ class AttentionGate(nn.Module):
         self.relu = nn.ReLU(inplace=True)
 
     def forward(self, g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        inter = self.W_g[0].weight.shape[0]
+        if inter % 16 != 0:
+            if inter % 8 != 0:
+                raise RuntimeError("AttentionGate needs an inter-channel count that is a multiple of 8")
+            view = _PaddedGate(self, 16 - inter % 16)
+            out = self._gate(view, g, x)
+            view.write_back()
+            return out
+        return self._gate(self, g, x)
+
+    @staticmethod
+    def _gate(m, g, x):
         if fp32.active():
-            return fp32.gate(self, g, x)
-        bg, bx, bp = self.W_g[1], self.W_x[1], self.psi[1]
-        return ops.AttentionGateFn.apply(g, x, self.W_g[0].weight, self.W_x[0].weight, self.psi[0].weight,
+            return fp32.gate(m, g, x)
+        bg, bx, bp = m.W_g[1], m.W_x[1], m.psi[1]
+        return ops.AttentionGateFn.apply(g, x, m.W_g[0].weight, m.W_x[0].weight, m.psi[0].weight,
                                          bg.weight, bg.bias, bx.weight, bx.bias, bp.weight, bp.bias,
                                          bg, bx, bp)
 

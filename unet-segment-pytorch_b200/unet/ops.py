@@ -31,8 +31,10 @@ def _grad_targets(*params):
         return None
     out = []
     for p in params:
+        if not getattr(p, "is_leaf", False):      # a padded / derived view of a parameter: through autograd
+            return None
         g = getattr(p, "grad", None)
-        if (g is None or not p.is_leaf or g.dtype != torch.float32 or not g.is_contiguous()
+        if (g is None or g.dtype != torch.float32 or not g.is_contiguous()
                 or g.numel() != p.numel() or g.device != p.device):
             return None
         out.append(g)
@@ -289,6 +291,10 @@ class AttentionGateFn(torch.autograd.Function):
             xp = K.conv_fwd(xn, wxf, 1)
             sg, hg, mg, ig = _bn_frozen_coeffs(bn_g)
             sx, hx, mx, ix = _bn_frozen_coeffs(bn_x)
+        if not batch and not need_grad and cx == 2 * wpsi.numel():
+            # inference: psi, sigmoid and the gating in one pass (csrc/gate.cu: gate_fused_eval_kernel)
+            sp, hp, _, _ = _bn_frozen_coeffs(bn_p)
+            return from_nhwc(K.gate_fused_eval(q, xp, xn, sg, hg, sx, hx, wpsi, sp, hp))
         psi, st_p = K.gate_psi(q, xp, sg, hg, sx, hx, wpsi, stats=batch)
         if batch:
             sp, hp, mp, ip = _bn_train_coeffs(st_p, count, bn_p)
