@@ -221,7 +221,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "steps_timed": len(times), "warmup": args.warmup, "ms_per_step": per * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": base_config(batch, 1),
+        # the arm's config is the GPU arm's for this N (what the driver pairs it with); the CPU process itself always
+        # runs one batch_per_gpu-sized step at a time: `sample`
+        "config": base_config(batch, max(1, args.gpus)),
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
