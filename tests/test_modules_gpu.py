@@ -557,3 +557,34 @@ def test_base_features_16_gate_with_8_inter_channels(precision):
         assert int(got_sd["up4.attention.W_g.1.num_batches_tracked"]) == int(sd["up4.attention.W_g.1.num_batches_tracked"]) + 1
     finally:
         unet.set_precision("bf16")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_second_device_while_first_is_current():
+    """The reference's get_device('cuda:1') pattern: the model and its inputs live on cuda:1 while the process's
+    current device stays cuda:0.  Every C-ABI call must run with the tensors' device current and on that device's
+    stream (unet/_C.py), and the launchers' one-time state is per device ordinal (csrc/conv.h: PerDevice)."""
+    from unet.models import AttentionUNet
+    from unet.utils.loss import DiceBCELoss
+    assert torch.cuda.current_device() == 0
+    torch.manual_seed(5)
+    m0 = AttentionUNet(1, 2, True, 32)
+    m1 = copy.deepcopy(m0).to("cuda:1").train()
+    m0 = m0.to("cuda:0").train()
+    x, t = O.synthetic_batch(2, 64, 64, seed=3, fg_fraction=0.05)
+    outs = []
+    for m, dev in ((m0, "cuda:0"), (m1, "cuda:1"), (m0, "cuda:0")):
+        if len(outs) == 2:
+            for p in m.parameters():
+                p.grad = None
+        out = m(x.to(dev))
+        assert out.device == torch.device(dev)
+        loss = DiceBCELoss()(out, t.to(dev))
+        loss.backward()
+        torch.cuda.synchronize(dev)
+        outs.append((out.detach().cpu(), [p.grad.detach().cpu() for p in m.parameters()]))
+    assert torch.cuda.current_device() == 0
+    (o0, g0), (o1, g1), _ = outs
+    assert torch.equal(o0, o1)
+    for a, b in zip(g0, g1):
+        assert torch.equal(a, b)
