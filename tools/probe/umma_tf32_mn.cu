@@ -2,6 +2,9 @@
 // needs: D[128 x 64] = sum_k A[k][m] * B[k][n], A = (64 pixels x 128 channels) fp32, B = (64 x 64) fp32, both
 // written by TMA as 32-channel (128-byte) sub-boxes with the 128-byte swizzle.  Variants of the descriptor
 // fields are tried; the one that reproduces the host result is what conv_wgrad.cu uses.
+// Measured on B200 (sm_100a, CUDA 12.9, driver 580): with the MN-major (transpose) bits set, kind::tf32 returns ZEROS for
+// both LBO/SBO assignments (no fault); without them it runs as K-major (a mismatch here, by construction).  kind::tf32 has
+// no MN-major operand mode on this part — the fp32 mode's weight gradient therefore uses bf16 hi/lo splits (fp32_train.cu).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -o tools/probe/umma_tf32_mn tools/probe/umma_tf32_mn.cu -lcuda
 #include <cmath>
 #include <cstdio>
