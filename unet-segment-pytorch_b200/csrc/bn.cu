@@ -84,10 +84,20 @@ static WinGeom make_geom(int N, int H, int W, int C) {
 }
 
 // ------------------------------------------------------------------------------ forward apply
+// fp32 pair -> packed bf16x2 with the ReLU folded into the conversion (one instruction instead of two max + one cvt)
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// POOL: also emit the 2x2 max-pooled copy (+ window index); RELU: compile-time so that the conversion carries it.
+// The decoder's ten launches per step have no pool: its compare / select work is not even compiled into theirs.
+template <bool POOL, bool RELU>
 __global__ void __launch_bounds__(kBnThreads, 4)
 bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __restrict__ scale,
               const float* __restrict__ shift, __nv_bfloat16* a, int ld_a, __nv_bfloat16* pooled,
-              int ld_p, unsigned char* pidx, int relu, WinGeom g) {
+              int ld_p, unsigned char* pidx, WinGeom g) {
   pdl_trigger();
   pdl_wait();
   const int lanes = blockDim.x / g.cgs;
@@ -132,23 +142,29 @@ bn_act_kernel(const __nv_bfloat16* __restrict__ y, int ld_y, const float* __rest
         F8 v = unpack8(raw[d]);
         uint4 packed;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          v.v[i] = fmaf(v.v[i], sc.v[i], sh.v[i]);
-          if (relu) v.v[i] = fmaxf(v.v[i], 0.f);
+        for (int i = 0; i < 8; ++i) v.v[i] = fmaf(v.v[i], sc.v[i], sh.v[i]);
+        if (RELU) {
+          packed.x = pack2_relu(v.v[0], v.v[1]);
+          packed.y = pack2_relu(v.v[2], v.v[3]);
+          packed.z = pack2_relu(v.v[4], v.v[5]);
+          packed.w = pack2_relu(v.v[6], v.v[7]);
+        } else {
+          packed = pack8(v);
         }
-        packed = pack8(v);
         if (a != nullptr) *reinterpret_cast<uint4*>(a + pix * ld_a + cg * 8) = packed;
-        const F8 r = unpack8(packed);
+        if (POOL) {
+          const F8 r = unpack8(packed);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (r.v[i] > mx.v[i]) {  // strict: the first maximum wins, as in ATen's max_pool2d
-            mx.v[i] = r.v[i];
-            arg[i] = d;
+          for (int i = 0; i < 8; ++i) {
+            if (r.v[i] > mx.v[i]) {  // strict: the first maximum wins, as in ATen's max_pool2d
+              mx.v[i] = r.v[i];
+              arg[i] = d;
+            }
           }
         }
       }
     }
-    if (pooled != nullptr && hc < Hp && wc < Wp) {
+    if (POOL && pooled != nullptr && hc < Hp && wc < Wp) {
       const size_t pp = (static_cast<size_t>(n) * Hp + hc) * Wp + wc;
       store8(pooled + pp * ld_p + cg * 8, mx);
       if (pidx != nullptr) {
@@ -365,7 +381,17 @@ int ub2_bn_act(const void* y, int ld_y, const float* scale, const float* shift, 
   const int block = bn_block(g.cgs);
   const int lanes = block / g.cgs;
   const int grid = stream_grid(g.windows, lanes, num_sms(), 8);
-  launch(bn_act_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, static_cast<__nv_bfloat16*>(a), ld_a, static_cast<__nv_bfloat16*>(pooled), ld_p, pidx, relu, g);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* yb = static_cast<const __nv_bfloat16*>(y);
+  __nv_bfloat16* ab = static_cast<__nv_bfloat16*>(a);
+  __nv_bfloat16* pb = static_cast<__nv_bfloat16*>(pooled);
+  if (pooled != nullptr) {
+    if (relu) launch(bn_act_kernel<true, true>, grid, block, 0, s, yb, ld_y, scale, shift, ab, ld_a, pb, ld_p, pidx, g);
+    else launch(bn_act_kernel<true, false>, grid, block, 0, s, yb, ld_y, scale, shift, ab, ld_a, pb, ld_p, pidx, g);
+  } else {
+    if (relu) launch(bn_act_kernel<false, true>, grid, block, 0, s, yb, ld_y, scale, shift, ab, ld_a, pb, ld_p, pidx, g);
+    else launch(bn_act_kernel<false, false>, grid, block, 0, s, yb, ld_y, scale, shift, ab, ld_a, pb, ld_p, pidx, g);
+  }
   return static_cast<int>(cudaGetLastError());
 }
 
