@@ -118,3 +118,34 @@ def test_conv_transpose2x2_and_pad_vs_torch(n, cin, h, w, ho, wo):
         mask = torch.ones(ho, wo, dtype=torch.bool)
         mask[py // 2: py // 2 + 2 * h, px // 2: px // 2 + 2 * w] = False
         assert (out.float().cpu()[:, :, mask] == 0).all()
+
+
+# n, hin, win, H, W, C — the statistics of up(q) computed on the low-resolution tensor (gate.cu,
+# gate_upstats_lowres_kernel) against sums over ATen's own interpolation (layers.py:98-102 feeding :107's BN)
+UPSTATS = [
+    (4, 32, 32, 64, 64, 256),      # up1 level, two channel groups per thread
+    (2, 64, 64, 128, 128, 128),
+    (1, 256, 256, 512, 512, 32),
+    (2, 37, 50, 75, 101, 16),      # ragged target size
+    (1, 20, 24, 47, 55, 64),
+    (1, 1, 1, 2, 2, 16),           # degenerate: every pixel is the one source pixel
+    (1, 1, 7, 3, 13, 16),
+    (3, 5, 1, 9, 4, 48),
+]
+
+
+@pytest.mark.parametrize("n,hin,win,h,w,c", UPSTATS)
+def test_gate_upstats_closed_form(n, hin, win, h, w, c):
+    from unet import kernels as K
+    torch.manual_seed(hin * 131 + w)
+    dev = torch.device("cuda:0")
+    q = (torch.randn(n, c, hin, win, device=dev) * 1.5 + 0.3).to(torch.bfloat16)
+    q_nhwc = K.empty_nhwc(n, hin, win, c, dev)
+    q_nhwc.copy_(q.permute(0, 2, 3, 1))
+    partials = K.gate_upstats(q_nhwc, h, w)
+    got = partials.sum(0)                                          # [2][C], fp64
+    up = F.interpolate(q.double(), size=(h, w), mode="bilinear", align_corners=True)
+    want = torch.stack([up.sum((0, 2, 3)), (up * up).sum((0, 2, 3))])
+    scale = torch.stack([up.abs().sum((0, 2, 3)), (up * up).sum((0, 2, 3))])
+    err = ((got - want).abs() / scale).max().item()
+    assert err < 2e-5, err                                         # fp32 per-thread sums, fp64 across threads
