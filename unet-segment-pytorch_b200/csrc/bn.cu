@@ -422,8 +422,8 @@ int ub2_bn_bwd_reduce(const void* dA, int ld_da, const void* dP, int ld_dp, cons
   BwdArgs a{static_cast<const __nv_bfloat16*>(dA), ld_da, static_cast<const __nv_bfloat16*>(dP), ld_dp, pidx,
             static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, nullptr, nullptr, 0, partials, relu};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (pool) launch(bn_bwd_kernel<true, false>, grid, block, smem, s, a, g);
-  else launch(bn_bwd_kernel<false, false>, grid, block, smem, s, a, g);
+  if (pool) launch_co(bn_bwd_kernel<true, false>, grid, block, smem, s, a, g);
+  else launch_co(bn_bwd_kernel<false, false>, grid, block, smem, s, a, g);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -431,7 +431,7 @@ int ub2_bn_bwd_finalize(const double* partials, int rows, int C, double count, c
                         const float* mean, const float* invstd, int frozen, float* dgamma, float* dbeta,
                         float* coef, void* stream) {
   if (C <= 0 || rows <= 0) return UB2_ERR_SHAPE;
-  launch(bn_bwd_finalize_kernel, (C + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream), partials, rows, C, count, gamma, mean, invstd, frozen, dgamma, dbeta, coef);
+  launch_co(bn_bwd_finalize_kernel, (C + 7) / 8, dim3(8, 128), 0, static_cast<cudaStream_t>(stream), partials, rows, C, count, gamma, mean, invstd, frozen, dgamma, dbeta, coef);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -450,8 +450,8 @@ int ub2_bn_bwd_apply(const void* dA, int ld_da, const void* dP, int ld_dp, const
             static_cast<const __nv_bfloat16*>(y), ld_y, scale, shift, coef,
             static_cast<__nv_bfloat16*>(dY), ld_dy, nullptr, relu};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (pool) launch(bn_bwd_kernel<true, true>, grid, block, 0, s, a, g);
-  else launch(bn_bwd_kernel<false, true>, grid, block, 0, s, a, g);
+  if (pool) launch_co(bn_bwd_kernel<true, true>, grid, block, 0, s, a, g);
+  else launch_co(bn_bwd_kernel<false, true>, grid, block, 0, s, a, g);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define UB2_ERR_SHAPE (-1)      /* unsupported shape */
 #define UB2_ERR_ALIGN (-2)      /* pointer / stride alignment */
@@ -90,6 +91,15 @@ int num_sms();
 // Resident CTA pairs a cluster kernel may use: the occupancy figure, capped by the SMs this process may fill
 // (UB2_RESERVE_SMS leaves SMs to co-running kernels of another stream — the NCCL all-reduce of a multi-GPU step).
 inline int cap_clusters(int occupancy_clusters) { const int c = num_sms() / 2; return occupancy_clusters < c ? occupancy_clusters : c; }
+// Shared-memory budget of a weight-gradient CTA (bytes).  The trainer runs weight gradients on a side stream next to
+// the bandwidth-bound BatchNorm passes of the following layer; those only find room on an SM if the resident
+// weight-gradient CTA leaves some shared memory (and it does leave 3/4 of the registers), and only under the common
+// 164 KB carveout of launch.cuh's launch_co().  Costs the deepest pipelines one or two stages (down1.3: 68 -> 72 us
+// alone, the others unchanged; 131 KB would double the 512^2 layers).  UB2_WGRAD_SMEM_KB.
+inline int wgrad_smem_budget() {
+  static const int kb = [] { const char* e = getenv("UB2_WGRAD_SMEM_KB"); int v = e ? atoi(e) : 163; return v < 64 ? 64 : (v > 227 ? 227 : v); }();
+  return kb * 1024;
+}
 // Which kernel the dispatcher picked for the calling thread's last convolution launch (tests assert it):
 // forward / dgrad 1 = conv_fwd (one CTA, per tap), 2 = conv_fwd2 (CTA pair, per tap), 3 = conv_halo (one CTA,
 // halo resident), 4 = conv_halo2 (CTA pair, halo resident); weight gradient 11..14 likewise.

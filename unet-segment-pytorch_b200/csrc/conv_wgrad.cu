@@ -272,7 +272,7 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   p.b_sub_bytes = kKPix * 64 * 2;
   const int b_subs = (BN + 63) / 64;
   p.stage_bytes = kWATileBytes + b_subs * p.b_sub_bytes;
-  int stages = (227 * 1024 - 1024 - static_cast<int>(sizeof(WgSmemHeader))) / p.stage_bytes;
+  int stages = (wgrad_smem_budget() - 1024 - static_cast<int>(sizeof(WgSmemHeader))) / p.stage_bytes;
   if (stages > kWMaxStages) stages = kWMaxStages;
   p.stages = stages;
 
@@ -319,7 +319,7 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   note_variant(11);
-  launch(conv_wgrad_kernel, grid, kWThreads, smem, stream, tmA0, tmA1, tmDY, p);
+  launch_co(conv_wgrad_kernel, grid, kWThreads, smem, stream, tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.splits_used) *a.splits_used = splits;

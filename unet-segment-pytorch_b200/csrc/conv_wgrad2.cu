@@ -279,7 +279,7 @@ int conv_wgrad2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   p.a_sub_bytes = kK2Pix * 64 * 2;
   p.b_sub_bytes = kK2Pix * 64 * 2;
   p.stage_bytes = kW2ATileBytes + (BN / 128) * p.b_sub_bytes;   // A tile + this CTA's half of the dy tile
-  int stages = (227 * 1024 - 1024 - static_cast<int>(sizeof(Wg2SmemHeader))) / p.stage_bytes;
+  int stages = (wgrad_smem_budget() - 1024 - static_cast<int>(sizeof(Wg2SmemHeader))) / p.stage_bytes;
   if (stages > kW2MaxStages) stages = kW2MaxStages;
   p.stages = stages;
 
@@ -330,7 +330,7 @@ int conv_wgrad2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   const int grid = 2 * (resident < total_items ? resident : total_items);
   const size_t smem = 1024 + static_cast<size_t>(stages) * p.stage_bytes + sizeof(Wg2SmemHeader);
   note_variant(12);
-  launch(conv_wgrad2_kernel, grid, kW2Threads, smem, stream, tmA0, tmA1, tmDY, p);
+  launch_co(conv_wgrad2_kernel, grid, kW2Threads, smem, stream, tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.splits_used) *a.splits_used = splits;

@@ -260,7 +260,7 @@ int conv_wgrad_halo_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   p.tmem_cols = tmem_cols;
   p.b_subs = (a.Cout + 63) / 64;
   p.b_stage_bytes = p.b_subs * 8192;
-  const int budget = 227 * 1024 - 1024 - static_cast<int>(sizeof(WgHaloHeader));
+  const int budget = wgrad_smem_budget() - 1024 - static_cast<int>(sizeof(WgHaloHeader));
   int R = a.H < 2 ? a.H : 2;
   p.a_bytes = ((64 * kGRW * (R + 2) * 2) + 1023) & ~1023;
   int b_stages = (budget - 2 * p.a_bytes) / p.b_stage_bytes;
@@ -308,7 +308,7 @@ int conv_wgrad_halo_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   note_variant(13);
-  launch(conv_wgrad_halo_kernel, grid, kGThreads, smem, stream, tmA0, tmA1, tmDY, p);
+  launch_co(conv_wgrad_halo_kernel, grid, kGThreads, smem, stream, tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.splits_used) *a.splits_used = splits;

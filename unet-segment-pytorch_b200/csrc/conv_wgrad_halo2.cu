@@ -298,7 +298,7 @@ int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   p.tmem_cols = tmem_cols;
   p.half = a.Cout / 2;
   p.b_stage_bytes = p.half * 2 * 64;   // 64 pixels x half the channels: 8 KB or 4 KB
-  const int budget = 227 * 1024 - 1024 - static_cast<int>(sizeof(WgHalo2Header));
+  const int budget = wgrad_smem_budget() - 1024 - static_cast<int>(sizeof(WgHalo2Header));
   int R = a.H < 2 ? a.H : 2;
   p.a_bytes = ((64 * kG2RW * (R + 2) * 2) + 1023) & ~1023;
   int b_stages = (budget - 2 * p.a_bytes) / p.b_stage_bytes;
@@ -357,7 +357,7 @@ int conv_wgrad_halo2_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   const size_t smem = 1024 + 2 * static_cast<size_t>(p.a_bytes) + static_cast<size_t>(b_stages) * p.b_stage_bytes +
                       sizeof(WgHalo2Header);
   note_variant(14);
-  launch(conv_wgrad_halo2_kernel, grid, kG2Threads, smem, stream, tmA0, tmA1, tmDY, p);
+  launch_co(conv_wgrad_halo2_kernel, grid, kG2Threads, smem, stream, tmA0, tmA1, tmDY, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   if (a.splits_used) *a.splits_used = splits;

@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <mutex>
+#include <set>
 #include <utility>
 
 namespace ub2 {
@@ -35,6 +37,35 @@ inline bool pdl_enabled() {
   return on;
 }
 
+// Shared-memory carveout of the kernels that are meant to run side by side on one SM.  An SM runs kernels of two
+// streams concurrently only if they agree on its L1 / shared-memory split; by default the driver picks the smallest
+// carveout that fits each kernel, so a streaming kernel (no shared memory, all L1) never becomes resident next to a
+// tensor-core kernel (227 KB carveout) even when registers and threads are free.  The trainer runs the weight-gradient
+// GEMMs on a side stream next to the BatchNorm-backward passes (ops.SideStream): both sides are launched with
+// launch_co(), which asks for the same split, 164 KB shared + 92 KB L1 (72 %).  Measured (tools/probe/overlap.py,
+// B200, batch 4): with 196 KB or more of shared memory the BatchNorm passes lose 12 % (a 60 KB L1 cannot hold the
+// loads a streaming kernel needs in flight), with 164 KB they run at full speed and the pair takes 81 us instead of
+// 100 (256-channel level), 69 instead of 89 (512).  UB2_CO_CARVEOUT=<percent> overrides, -1 leaves the driver's choice.
+inline int co_carveout_percent() {
+  static const int pct = [] {
+    const char* e = getenv("UB2_CO_CARVEOUT");
+    const int v = e ? atoi(e) : 72;
+    return v > 100 ? 100 : v;
+  }();
+  return pct;
+}
+
+inline void apply_carveout(const void* kernel, int pct) {
+  if (pct < 0) return;
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  (void)cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.insert({dev, kernel}).second)
+    (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -48,6 +79,13 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors: cudaGetLastError() at the call site
+}
+
+// launch() for a kernel that shares SMs with a kernel of another stream (see co_carveout_percent()).
+template <typename... KArgs, typename... Args>
+inline void launch_co(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  apply_carveout(reinterpret_cast<const void*>(kernel), co_carveout_percent());
+  launch(kernel, grid, block, smem, stream, std::forward<Args>(args)...);
 }
 
 }  // namespace ub2

@@ -57,6 +57,45 @@ def _reduce_into(param, partial, cout, cin, taps, target):
         GRAD_SINK(param)
 
 
+# Weight gradients off the critical path.  In backward a layer's data gradient feeds the next layer's BatchNorm
+# backward, its weight gradient feeds nothing until the bucket fold — yet both are tensor-pipe kernels that were
+# queued one behind the other in front of the bandwidth-bound BatchNorm passes.  With a side stream installed
+# (BatchShardedTrainer does it together with the sink) the weight-gradient GEMM of layer L runs next to the
+# BatchNorm-backward reduce / apply passes of layer L-1: the data gradient is queued first on the main stream,
+# the weight gradient forks behind the same dy, and the main stream joins again before the next fork and before
+# any fold of the partial tiles.  Inside a CUDA-graph capture the fork and join become graph edges.
+# Tensors the side stream reads (dy and the saved activations) are kept referenced until the join, because the
+# caching allocator reuses a freed block in main-stream order only.
+class SideStream:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self._keep = None
+
+    def run(self, fn, *keep):
+        main = torch.cuda.current_stream()
+        self.join()
+        self.stream.wait_stream(main)
+        with torch.cuda.stream(self.stream):
+            out = fn()
+        self._keep = (keep, out)
+        return out
+
+    def join(self):
+        if self._keep is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self._keep = None
+
+
+WGRAD_SIDE = None
+
+
+def wgrad_join():
+    """Main stream waits for the weight gradients still running on the side stream (before their partial tiles
+    are folded, and at the end of backward)."""
+    if WGRAD_SIDE is not None:
+        WGRAD_SIDE.join()
+
+
 # Weight packs prepared for the current step by a ``kernels.WeightPacker`` (installed by
 # BatchShardedTrainer after it has rebuilt them in one launch); None -> pack per call.
 PACKS = None
@@ -157,15 +196,7 @@ class ConvBnRelu(torch.autograd.Function):
                                          targets=bn_t)
         if bn_t is not None:
             _grads_done(p_gamma, p_beta)
-        gw = None
-        if ctx.needs_input_grad[2]:
-            part = K.conv_wgrad(a0, dy, taps, x1=a1)
-            w_t = _grad_targets(p_w)
-            if w_t is not None:
-                _reduce_into(p_w, part, cout, cin, taps, w_t[0])
-            else:
-                gw = torch.empty(wshape, device=dy.device, dtype=torch.float32)
-                K.wgrad_reduce(part, cout, cin, taps, gw)
+        # data gradient first: it is what the next layer's backward waits for
         d0 = d1 = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             n, h, w, _ = a0.shape
@@ -175,6 +206,18 @@ class ConvBnRelu(torch.autograd.Function):
             K.conv_fwd(dy, wd, taps, out=d0, out1=d1, split=c0)
             d0 = from_nhwc(d0)
             d1 = from_nhwc(d1) if d1 is not None else None
+        gw = None
+        if ctx.needs_input_grad[2]:
+            w_t = _grad_targets(p_w)
+            if w_t is not None and WGRAD_SIDE is not None and getattr(GRAD_SINK, "defer_reduce", None) is not None:
+                part = WGRAD_SIDE.run(lambda: K.conv_wgrad(a0, dy, taps, x1=a1), a0, a1, dy)
+            else:
+                part = K.conv_wgrad(a0, dy, taps, x1=a1)
+            if w_t is not None:
+                _reduce_into(p_w, part, cout, cin, taps, w_t[0])
+            else:
+                gw = torch.empty(wshape, device=dy.device, dtype=torch.float32)
+                K.wgrad_reduce(part, cout, cin, taps, gw)
         return d0, d1, gw, dgamma, dbeta, None, None
 
 

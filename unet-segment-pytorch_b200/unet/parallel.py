@@ -17,6 +17,7 @@ code runs without collectives.
 """
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
@@ -87,7 +88,6 @@ class BatchShardedTrainer:
         #   UB2_SKIP_ALLREDUCE=1   run the multi-rank step WITHOUT its collectives (replicas then diverge)
         #   UB2_ALLREDUCE_AT_END=1 launch every bucket's all-reduce after backward instead of as it fills
         #   UB2_BUCKET_MB=<float>  bucket size override
-        import os
         self._skip_collectives = os.environ.get("UB2_SKIP_ALLREDUCE", "0") == "1"
         self._collectives_at_end = os.environ.get("UB2_ALLREDUCE_AT_END", "0") == "1"
         bucket_mb = float(os.environ.get("UB2_BUCKET_MB", bucket_mb))
@@ -115,6 +115,8 @@ class BatchShardedTrainer:
         self._graphs = {}
         self._eager_steps = {}
         self._copy_stream = None   # mask copies (see step)
+        self._side = None          # weight gradients next to the BatchNorm passes (ops.SideStream)
+        self._side_enabled = os.environ.get("UB2_WGRAD_SIDE", "1") != "0"
         self._masks_ready = self._step_done = None
 
     # ------------------------------------------------------------------ replicated state
@@ -181,6 +183,7 @@ class BatchShardedTrainer:
             # every other gradient of the bucket is in: fold all its split-K partials in one go
             from .kernels import wgrad_reduce_multi
             items, bucket.deferred = bucket.deferred, []
+            ops.wgrad_join()   # the last partial tiles may still be written on the side stream
             wgrad_reduce_multi(items, accumulate=True)
             bucket.pending -= len(items)
         if (bucket.pending == 0 and self.world > 1 and self._last and bucket.work is None
@@ -200,6 +203,7 @@ class BatchShardedTrainer:
     def _flush_deferred(self) -> None:
         """End of backward: buckets in which some parameter received no gradient this step."""
         from .kernels import wgrad_reduce_multi
+        ops.wgrad_join()
         for b in self.buckets:
             if b.deferred:
                 items, b.deferred = b.deferred, []
@@ -247,16 +251,30 @@ class BatchShardedTrainer:
         """Second half: loss, backward (gradient sink installed) and, on the last micro-batch of an
         optimizer step, all-reduce, clip + optimizer, EMA."""
         prev_sink, ops.GRAD_SINK = ops.GRAD_SINK, _GradSink(self)
+        prev_side, ops.WGRAD_SIDE = ops.WGRAD_SIDE, self._wgrad_side(outputs)
         try:
             loss = self.criterion(outputs, masks)
             (loss / (self.world * self.accumulation_steps)).backward()
             self._flush_deferred()
         finally:
+            ops.wgrad_join()
             ops.GRAD_SINK = prev_sink
+            ops.WGRAD_SIDE = prev_side
         if not self._last:
             return loss.detach()
         self._optimizer_tail()
         return loss.detach()
+
+    def _wgrad_side(self, outputs):
+        """The side stream weight gradients run on (ops.SideStream), or None: UB2_WGRAD_SIDE=0, CPU."""
+        if not self._side_enabled:
+            return None
+        t = outputs[0] if isinstance(outputs, (tuple, list)) else outputs
+        if not (torch.is_tensor(t) and t.is_cuda):
+            return None
+        if self._side is None or self._side.stream.device != t.device:
+            self._side = ops.SideStream(t.device)
+        return self._side
 
     def _optimizer_tail(self) -> None:
         """All-reduce what is not in flight yet, wait, clip + optimizer step, EMA (train.py:139-147)."""
@@ -361,9 +379,14 @@ class BatchShardedTrainer:
             # two graphs sharing one memory pool, always replayed in this order: forward | the rest.
             # Between them the main stream waits for the masks.
             g_fwd, g_bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_fwd):
+            cap = None
+            if os.environ.get("UB2_CAPTURE_PRIORITY", "0") == "1":
+                # the critical path (everything but the weight gradients) on a high-priority stream: its thread
+                # blocks are dispatched ahead of the side stream's whenever both have work ready
+                cap = torch.cuda.Stream(device=dev, priority=-1)
+            with torch.cuda.graph(g_fwd, stream=cap):
                 outputs = self._forward(gx)
-            with torch.cuda.graph(g_bwd, pool=g_fwd.pool()):
+            with torch.cuda.graph(g_bwd, pool=g_fwd.pool(), stream=cap):
                 gloss = self._backward(outputs, gt)
             del outputs
             entry = self._graphs[key] = (g_fwd, g_bwd, gx, gt, gloss)
