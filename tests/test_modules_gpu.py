@@ -329,6 +329,35 @@ def test_cuda_graph_step_equals_eager():
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_weight_gradients_on_the_side_stream_change_nothing(use_graph, monkeypatch):
+    """ops.SideStream: the weight-gradient GEMMs forked next to the BatchNorm-backward passes produce the same
+    bits as the one-stream order (same kernels, same split-K; only the schedule differs), eager and replayed,
+    over enough steps that a premature fold or a recycled dy would show."""
+    from unet import ops
+    from unet.models import AttentionUNet
+    from unet.parallel import BatchShardedTrainer
+    from unet.optim import FusedAdamW
+    from unet.utils.loss import DiceBCELoss
+    x, t = O.synthetic_batch(2, 96, 64, seed=11, fg_fraction=0.05)
+    x, t = x.cuda(), t.cuda()
+    results = []
+    for side in ("0", "1"):
+        monkeypatch.setenv("UB2_WGRAD_SIDE", side)
+        torch.manual_seed(5)
+        model = AttentionUNet(1, 2, True, 32).cuda()
+        tr = BatchShardedTrainer(model, DiceBCELoss(), FusedAdamW(model.parameters(), lr=1e-3), grad_clip=1.0,
+                                 cuda_graph=use_graph, graph_warmup=2)
+        assert (tr._wgrad_side(x) is not None) == (side == "1")
+        losses = [tr.step(x, t).item() for _ in range(8)]
+        assert ops.WGRAD_SIDE is None                       # installed for the duration of backward only
+        results.append((losses, [p.detach().clone() for p in model.parameters()]))
+    (l0, p0), (l1, p1) = results
+    assert l0 == l1, (l0, l1)
+    for a, b in zip(p0, p1):
+        assert torch.equal(a, b)
+
+
 def test_accumulation_steps_graph_equals_eager_and_autograd():
     """accumulation_steps=2 (train.py:127-147 on one GPU): replayed graphs (one per micro-batch phase)
     == eager, and the accumulated gradient equals plain autograd's sum over the two micro-batches."""
