@@ -72,7 +72,7 @@ class SideStream:
         self._keep = None
 
     def run(self, fn, *keep):
-        main = torch.cuda.current_stream()
+        main = torch.cuda.current_stream(self.stream.device)
         self.join()
         self.stream.wait_stream(main)
         with torch.cuda.stream(self.stream):
@@ -82,7 +82,7 @@ class SideStream:
 
     def join(self):
         if self._keep is not None:
-            torch.cuda.current_stream().wait_stream(self.stream)
+            torch.cuda.current_stream(self.stream.device).wait_stream(self.stream)
             self._keep = None
 
 
