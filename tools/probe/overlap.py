@@ -1,7 +1,11 @@
 """Probe: does a weight-gradient GEMM overlap with the BatchNorm-backward passes when they run on two streams?
 For one layer shape: time wgrad alone, the BN-backward trio alone, both back to back on one stream, and both
 forked onto two streams, all as CUDA-graph replays (the step's execution mode).
-    UB2_WGRAD_SMEM_KB=196 python tools/probe/overlap.py [batch]
+    python tools/probe/overlap.py [batch]                                             # today's defaults: they overlap
+    UB2_CO_CARVEOUT=-1 UB2_WGRAD_SMEM_KB=227 python tools/probe/overlap.py [batch]    # round-2 start: forked == serial
+MEASURED (profiles/r02_side_stream.md; the runs there used a probe-time knob UB2_CARVEOUT that set one carveout for
+EVERY kernel — replaced since by launch_co() on the kernels that share an SM): the pair overlaps only when both
+kernels request the same shared-memory carveout, and the BatchNorm passes keep their speed only with <= 164 KB of it.
 """
 import os
 import sys
