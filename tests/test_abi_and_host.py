@@ -196,3 +196,58 @@ def test_convolution_kernels_are_tcgen05_tma_code():
     for k, ops in conv.items():
         assert {"UTCHMMA", "LDTM", "UTMALDG", "UTCBAR"} <= ops, (k, ops)
     assert not any("legacy HMMA" in ops for ops in per_kernel.values())
+
+
+def test_side_stream_fork_join_bookkeeping(monkeypatch):
+    """ops.SideStream on fake streams (no GPU here): the side stream waits for the main stream before each fork, the
+    main stream joins the previous fork before the next one, and the tensors a fork reads stay referenced until
+    that join — the caching allocator recycles a freed block in main-stream order only."""
+    import weakref
+    from unet import ops
+    log = []
+
+    class FakeStream:
+        def __init__(self, name="side", device=None):
+            self.name, self.device = name, device
+
+        def wait_stream(self, other):
+            log.append((self.name, "waits", other.name))
+
+    class FakeCtx:
+        def __init__(self, s):
+            self.s = s
+
+        def __enter__(self):
+            log.append(("enter", self.s.name))
+
+        def __exit__(self, *a):
+            log.append(("exit", self.s.name))
+
+    main = FakeStream("main")
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: FakeStream("side", device))
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: main)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: FakeCtx(s))
+
+    class Blob:   # stands for a tensor (weak-referenceable)
+        pass
+
+    side = ops.SideStream("cuda:0")
+    a, dy = Blob(), Blob()
+    ra, rdy = weakref.ref(a), weakref.ref(dy)
+    out = side.run(lambda: log.append("wgrad-1") or "partials-1", a, dy)
+    assert out == "partials-1"
+    assert log == [("side", "waits", "main"), ("enter", "side"), "wgrad-1", ("exit", "side")]
+    del a, dy
+    assert ra() is not None and rdy() is not None          # still referenced: the side stream may be reading them
+    del log[:]
+    side.run(lambda: log.append("wgrad-2"), Blob())
+    # the main stream joined fork 1 BEFORE fork 2 was queued, and fork 1's operands were released at that join
+    assert log[0] == ("main", "waits", "side") and log[1] == ("side", "waits", "main") and "wgrad-2" in log
+    assert ra() is None and rdy() is None
+    del log[:]
+    side.join()
+    side.join()                                             # idempotent: nothing outstanding after the first
+    assert log == [("main", "waits", "side")]
+    # module-level join is a no-op without an installed side stream
+    assert ops.WGRAD_SIDE is None
+    ops.wgrad_join()
