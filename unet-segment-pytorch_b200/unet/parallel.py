@@ -117,6 +117,9 @@ class BatchShardedTrainer:
         self._copy_stream = None   # mask copies (see step)
         self._side = None          # weight gradients next to the BatchNorm passes (ops.SideStream)
         self._side_enabled = os.environ.get("UB2_WGRAD_SIDE", "1") != "0"
+        dev0 = next(model.parameters()).device
+        if self._side_enabled and dev0.type == "cuda":
+            self._side = ops.SideStream(dev0)   # created here, never inside a graph capture
         self._masks_ready = self._step_done = None
 
     # ------------------------------------------------------------------ replicated state
